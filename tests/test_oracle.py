@@ -1,0 +1,248 @@
+"""Pins the CPU oracle (CPU-only tests, no GPU).
+
+1. golden: every known-answer vector the reference's own tests hold for the hot
+   path (tests/golden/reference_vectors.json), at the tolerance the reference's
+   assertion uses -- run through the C restatement and, when built, through the
+   reference headers themselves.
+2. fixtures: the C restatement must reproduce, bit for bit, the outputs the
+   reference produced in the build container (tests/golden/ref_outputs.npz,
+   made by tests/golden/make_fixtures.py), edge cases included.
+3. live: where oracle/_ref is present, bit-for-bit equality on larger seeded
+   batches.
+"""
+import numpy as np
+import pytest
+
+from matrix_b200 import synth
+
+EPS_SP = float(np.finfo(np.float32).eps)
+
+
+def bits_equal(a, b):
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    if a.dtype == np.float64:
+        # NaNs never appear in these workloads; compare raw bit patterns
+        return a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    return np.array_equal(a, b)
+
+
+@pytest.fixture(params=["port", "ref"])
+def oracle(request):
+    return request.getfixturevalue(request.param)
+
+
+# ----------------------------------------------------------------------------- 1. golden vectors
+def test_golden_hat(oracle, golden):
+    g = golden["hat_so3"]
+    ad = oracle.se3_adt(np.array(g["vec"] + [0, 0, 0], dtype=float)).reshape(6, 6).T  # [r, c]
+    hat = ad[:3, :3].T.reshape(9)  # column-major
+    assert np.max(np.abs(hat - np.array(g["expected"], dtype=float))) < g["tol"]
+
+
+def test_golden_so3_rotz_sweep(oracle, golden):
+    g = golden["so3_rotz_sweep"]
+    deg = np.arange(g["degrees_from"], g["degrees_to"] + 1, dtype=float)
+    th = deg * 3.141592653589793 / 180.0
+    w = np.stack([np.zeros_like(th), np.zeros_like(th), th], axis=1)
+    R = oracle.so3_exp(w)
+    rotz = np.stack([np.cos(th), np.sin(th), 0 * th, -np.sin(th), np.cos(th), 0 * th, 0 * th, 0 * th, 1 + 0 * th], axis=1)
+    assert np.max(np.abs(R - rotz)) < g["tol"]
+    back = oracle.SO3_log(R)
+    assert np.max(np.linalg.norm(back - w, axis=1)) < g["tol"]
+
+
+def test_golden_SE3_log(oracle, golden):
+    g = golden["SE3_log"]
+    xi = oracle.SE3_log(np.array(g["T"], dtype=float))[0]
+    m = np.array(g["expected_hat"])
+    vee = np.array([m[6], m[8], m[1], m[12], m[13], m[14]])
+    assert np.max(np.abs(xi - vee)) < g["tol"]
+
+
+def test_golden_se3_exp(oracle, golden):
+    g = golden["se3_exp"]
+    m = np.array(g["se3mat"])
+    xi = np.array([m[6], m[8], m[1], m[12], m[13], m[14]])
+    T = oracle.se3_exp(xi)[0].reshape(4, 4).T
+    R = np.array(g["expected_R"], dtype=float).reshape(3, 3).T
+    assert np.max(np.abs(T[:3, :3] - R)) < g["tol"]
+    assert np.max(np.abs(T[:3, 3] - np.array(g["expected_p"], dtype=float))) < g["tol"]
+    assert np.array_equal(T[3], [0, 0, 0, 1])
+
+
+def test_golden_ur5(oracle, golden):
+    g = golden["ur5"]
+    S = np.array(g["screws"], dtype=float)
+    M = np.array(g["home"])
+    assert np.array_equal(S, synth.UR5_SCREWS) and np.array_equal(M, synth.UR5_HOME)
+    q = np.array(g["q_times_pi"]) * 3.141592653589793
+    T, Js = oracle.poe_fk_jacobian(S, M, q)
+    assert np.max(np.abs(T[0] - np.array(g["fk"]))) < g["tol"]
+    J = Js[0].reshape(6, 6)  # row i = column i of the Jacobian
+    assert np.array_equal(J[0], S[0])  # demo/robotics.hpp:97
+    assert np.max(np.abs(J[1:] - np.array(g["jacobian_cols_1_to_5"]))) < g["tol"]
+    qs, it = oracle.ik_solve(S, M, np.array(g["ik_start"]), np.array(g["ik_target"]), g["ik_max_iter"])
+    Tq, _ = oracle.poe_fk_jacobian(S, M, qs, want_Js=False)
+    assert np.max(np.abs(Tq[0] - np.array(g["ik_target"]))) < g["tol"]
+    assert 1 <= it[0] <= g["ik_max_iter"]
+
+
+def test_golden_linsolve(oracle, golden):
+    g = golden["linsolve_4x3"]
+    A, b, x = np.array(g["A"]), np.array(g["b"], dtype=float), np.array(g["x"])
+    xq, st = oracle.linsolve_qr(4, 3, A, b)
+    assert st[0] == 0 and np.max(np.abs(xq[0] - x)) < g["tol"]
+    assert np.max(np.abs(oracle.linsolve_svd(4, 3, A, b)[0] - x)) < g["tol"]
+    # the literal carries 15 digits: both solvers agree with it far below the reference's own tolerance
+    assert np.max(np.abs(xq[0] - x)) < 5e-15
+
+
+def test_golden_svd_reconstruct(oracle, golden):
+    g = golden["svd_reconstruct_4x3"]
+    A = np.array(g["A"], dtype=float)
+    U, w, V = oracle.svd(4, 3, A)
+    rec = U[0].reshape(3, 4).T @ np.diag(w[0]) @ V[0].reshape(3, 3)  # V[0].reshape = V^T
+    assert np.max(np.abs(rec - A.reshape(3, 4).T)) < g["tol"]
+
+
+def test_golden_eig(oracle, golden):
+    g = golden["eig_sym_4"]
+    d, z = oracle.eig_sym(4, np.array(g["S"], dtype=float), sorted=True)
+    assert np.max(np.abs(d[0] - np.array(g["d"]))) < g["tol"]
+    lit = np.array(g["z_literal"])
+    expected = np.array([-lit[c + 4 * r] for c in range(4) for r in range(4)])  # index r + 4c
+    assert np.max(np.abs(z[0] - expected)) < g["tol"]
+
+
+def test_golden_matrix_norm2(oracle, golden):
+    g = golden["matrix_norm2"]
+    for case in g["cases"]:
+        if oracle.kind == "reference" and (case["m"], case["n"]) not in [(5, 4), (4, 5), (4, 4)]:
+            continue
+        s = oracle.norm2(case["m"], case["n"], np.array(case["A"]))
+        assert abs(s[0] - case["norm2"]) < g["tol"]
+
+
+def test_golden_inverse(oracle, golden):
+    g = golden["inverse_2x2"]
+    A = np.array(g["A"], dtype=float)
+    assert np.max(np.abs(oracle.inverse(2, A)[0] - np.array(g["inverse"]))) < g["tol"]
+    assert abs(oracle.det(2, A)[0] - g["det"]) < 2.3e-16 * 5
+
+
+# ----------------------------------------------------------------------------- 2. committed reference outputs
+def _replay(o, fx):
+    """Every op through oracle `o` on the fixture inputs -> dict with the fixture's keys."""
+    S, M = synth.UR5_SCREWS, synth.UR5_HOME
+    out = {}
+    xi = fx["se3_exp.xi"]
+    out["se3_exp.T"] = o.se3_exp(xi)
+    out["SE3_log.xi"] = o.SE3_log(fx["SE3_log.T"])
+    out["se3_exp_log.xi"] = o.se3_exp_log(xi)
+    out["so3_exp.R"] = o.so3_exp(fx["so3_exp.w"])
+    out["SO3_log.w"] = o.SO3_log(fx["SO3_log.R"])
+    for k, nm in enumerate(["ljac", "ljacinv", "rjac", "rjacinv"]):
+        out[f"so3_{nm}.J"] = o.so3_jac(k, fx["so3_exp.w"])
+    out["SE3_mul.C"] = o.SE3_mul(fx["SE3_mul.A"], fx["SE3_mul.B"])
+    out["SE3_inv.Ti"] = o.SE3_inv(fx["SE3_mul.A"])
+    out["SE3_Adt.Ad"] = o.SE3_Adt(fx["SE3_mul.A"])
+    out["se3_adt.ad"] = o.se3_adt(xi)
+    out["ur5.T"], out["ur5.Js"] = o.poe_fk_jacobian(S, M, fx["ur5.q"])
+    for nj in (4, 7):
+        out[f"chain{nj}.T"], out[f"chain{nj}.Js"] = o.poe_fk_jacobian(
+            fx[f"chain{nj}.screws"], fx[f"chain{nj}.home"], fx[f"chain{nj}.q"])
+    A, b = fx["lstsq.A"], fx["lstsq.b"]
+    out["lstsq.x_qr"], out["lstsq.status_qr"] = o.linsolve_qr(4, 3, A, b)
+    out["lstsq.x_svd"] = o.linsolve_svd(4, 3, A, b)
+    out["lstsq.U"], out["lstsq.w"], out["lstsq.V"] = o.svd(4, 3, A)
+    out["lstsq.pinv"] = o.pinv(4, 3, A)
+    A6, b6 = fx["dense6.A"], fx["dense6.b"]
+    out["dense6.U"], out["dense6.w"], out["dense6.V"] = o.svd(6, 6, A6)
+    out["dense6.x_svd"] = o.linsolve_svd(6, 6, A6, b6)
+    out["dense6.x_qr"], out["dense6.status_qr"] = o.linsolve_qr(6, 6, A6, b6)
+    out["dense6.x_lu"], out["dense6.status_lu"] = o.linsolve_lu(6, A6, b6)
+    out["dense6.inverse"] = o.inverse(6, A6)
+    out["dense6.det"] = o.det(6, A6)
+    out["dense6.norm2"] = o.norm2(6, 6, A6)
+    out["sym4.d_sorted"], out["sym4.z_sorted"] = o.eig_sym(4, fx["sym4.S"], True)
+    out["sym4.d_unsorted"], out["sym4.z_unsorted"] = o.eig_sym(4, fx["sym4.S"], False)
+    out["sym6.d_sorted"], out["sym6.z_sorted"] = o.eig_sym(6, fx["sym6.S"], True)
+    out["ik.q_out"], out["ik.Vs"] = o.ik_newton_step(S, M, fx["ik.q"], fx["ik.Ttarget"])
+    out["ik.q_solved"], out["ik.iters"] = o.ik_solve(S, M, fx["ik.q"], fx["ik.Ttarget"], 20)
+    return out
+
+
+def test_port_reproduces_reference_fixtures_bit_for_bit(port, fixtures):
+    got = _replay(port, fixtures)
+    bad = [k for k, v in got.items() if not bits_equal(v, fixtures[k])]
+    assert not bad, f"C restatement differs from the reference's recorded outputs in: {bad}"
+    assert len(got) >= 40
+
+
+def test_fixture_edge_cases_hit_every_branch(fixtures):
+    """The recorded reference outputs really contain the branches the parity tests rely on."""
+    xi, T = fixtures["se3_exp.xi"], fixtures["se3_exp.T"]
+    phi = np.linalg.norm(xi[:, :3], axis=1)
+    small = phi < EPS_SP
+    assert small.sum() >= 5 and (~small).sum() >= 100
+    ident = np.eye(4).T.reshape(16).copy()
+    for row, x in zip(T[small], xi[small]):
+        e = ident.copy()
+        e[12:15] = x[3:]
+        assert np.array_equal(row, e)  # liegroup.hpp:258-261
+    # SE3::log at theta = pi returns a zero rotation part (liegroup.hpp:246-249)
+    lg = fixtures["SE3_log.xi"]
+    tr = T[:, 0] + T[:, 5] + T[:, 10]
+    at_pi = np.abs((tr - 1) / 2) >= 1
+    assert at_pi.sum() >= 5 and np.all(lg[at_pi][:, :3] == 0)
+    # SO3::log pi-branch: all three sub-cases (liegroup.hpp:68-84)
+    w = fixtures["SO3_log.w"][1:4]
+    assert np.allclose(np.abs(w), np.pi * np.eye(3))
+    # QR flags singular systems and returns b untouched (linalg.hpp:549-552, 1195-1199)
+    st = fixtures["lstsq.status_qr"]
+    assert set(np.unique(st)) == {0, 3}
+    sing = st == 3
+    assert np.array_equal(fixtures["lstsq.x_qr"][sing], fixtures["lstsq.b"][sing][:, :3])
+    assert set(np.unique(fixtures["dense6.status_lu"])) == {0, 3}
+    assert fixtures["ik.iters"].max() <= 20 and fixtures["ik.iters"].min() >= 1
+
+
+# ----------------------------------------------------------------------------- 3. live, larger batches
+def test_port_matches_reference_live(port, ref_strict):
+    n = 20000
+    S, M = synth.UR5_SCREWS, synth.UR5_HOME
+    xi = synth.se3_twists(n, first=1000)
+    assert bits_equal(port.se3_exp(xi), ref_strict.se3_exp(xi))
+    T = ref_strict.se3_exp(xi)
+    assert bits_equal(port.SE3_log(T), ref_strict.SE3_log(T))
+    q = synth.joint_angles(n, first=1000)
+    a, b = port.poe_fk_jacobian(S, M, q), ref_strict.poe_fk_jacobian(S, M, q)
+    assert bits_equal(a[0], b[0]) and bits_equal(a[1], b[1])
+    A, rhs = synth.lstsq_4x3(n, first=1000)
+    a, b = port.linsolve_qr(4, 3, A, rhs), ref_strict.linsolve_qr(4, 3, A, rhs)
+    assert bits_equal(a[0], b[0]) and bits_equal(a[1], b[1])
+    A6 = synth.dense(n, 6, 6, first=1000)
+    for x, y in zip(port.svd(6, 6, A6), ref_strict.svd(6, 6, A6)):
+        assert bits_equal(x, y)
+    S4 = synth.symmetric(n, 4, first=1000)
+    for x, y in zip(port.eig_sym(4, S4), ref_strict.eig_sym(4, S4)):
+        assert bits_equal(x, y)
+    qi = synth.joint_angles(n, first=1000, seed=synth.SEEDS["ik_newton_step"])
+    Tt = ref_strict.poe_fk_jacobian(S, M, qi + synth.ik_offsets(n, first=1000), want_Js=False)[0]
+    for x, y in zip(port.ik_newton_step(S, M, qi, Tt), ref_strict.ik_newton_step(S, M, qi, Tt)):
+        assert bits_equal(x, y)
+
+
+def test_release_reference_build_is_within_fp_noise_of_strict(ref, ref_strict):
+    """libppx_ref.so (FMA contraction on, the CPU baseline) vs the strict build: SURVEY.md section 0.5."""
+    n = 20000
+    xi = synth.se3_twists(n)
+    a, b = ref.se3_exp_log(xi), ref_strict.se3_exp_log(xi)
+    # the round trip amplifies last-bit differences in R by ~1/sin^2(theta): 1.5e-13 at theta = pi - 0.05
+    assert np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b).max(axis=1, keepdims=True))) < 1e-12
+    T = ref_strict.se3_exp(xi)
+    assert np.max(np.abs(ref.SE3_log(T) - ref_strict.SE3_log(T))) < 1e-14  # same inputs: 4e-16
+    q = synth.joint_angles(n)
+    a, b = ref.poe_fk_jacobian(synth.UR5_SCREWS, synth.UR5_HOME, q), ref_strict.poe_fk_jacobian(synth.UR5_SCREWS, synth.UR5_HOME, q)
+    assert np.max(np.abs(a[0] - b[0])) < 1e-13 and np.max(np.abs(a[1] - b[1])) < 1e-13
