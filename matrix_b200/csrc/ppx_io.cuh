@@ -1,0 +1,163 @@
+// ppx_io.cuh -- how a batch of fixed-size records moves between HBM and the registers of the
+// thread that owns the instance.
+//
+//   SOA  component-major, base[k*ld + i].  Component k of 32 consecutive instances is 256
+//        contiguous bytes, so every warp-level access is two full 128-byte lines: coalesced by
+//        construction, no staging.  Loads use ld.global.cs / stores st.global.cs (evict-first):
+//        every byte is touched exactly once per launch and must not displace anything in L2.
+//   AOS  dense reference records, base[i*D + k] (std::vector<ppx::MatrixS<M,N>>::data()).  A
+//        thread-per-record access would touch 32 different sectors per instruction, so each warp
+//        moves its 32 records (one contiguous 32*D*8-byte span) with coalesced accesses through a
+//        private shared-memory tile whose record stride is padded to an odd number of doubles;
+//        the per-thread side of the transpose is then bank-conflict free.  Only __syncwarp is
+//        needed: warps never wait for each other.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+
+namespace ppx_dev
+{
+
+constexpr int LAYOUT_AOS = 0;
+constexpr int LAYOUT_SOA = 1;
+
+template <int LAYOUT>
+struct TileIO;
+
+template <>
+struct TileIO<LAYOUT_SOA>
+{
+    size_t i;   // this thread's instance
+    size_t ld;  // component stride
+    bool valid; // i < n
+
+    static constexpr size_t smem_bytes(int /*block*/, int /*max_width*/) { return 0; }
+
+    __device__ __forceinline__ TileIO(size_t tile_base, size_t n, size_t ld_, double * /*smem*/, int /*max_width*/)
+        : i(tile_base + threadIdx.x), ld(ld_), valid(tile_base + threadIdx.x < n) {}
+
+    template <int D>
+    __device__ __forceinline__ void load(const double *__restrict__ base, double (&r)[D]) const
+    {
+#pragma unroll
+        for (int k = 0; k < D; k++)
+            r[k] = valid ? __ldcs(base + (size_t)k * ld + i) : 0.0;
+    }
+
+    template <int D>
+    __device__ __forceinline__ void store(double *__restrict__ base, const double (&r)[D]) const
+    {
+        if (valid)
+        {
+#pragma unroll
+            for (int k = 0; k < D; k++)
+                __stcs(base + (size_t)k * ld + i, r[k]);
+        }
+    }
+
+    // piecewise store of a D-wide record: components off .. off+CNT-1 now, flush<D>() once at the end
+    template <int D, int CNT>
+    __device__ __forceinline__ void put(double *__restrict__ base, int off, const double (&r)[CNT]) const
+    {
+        if (valid)
+        {
+#pragma unroll
+            for (int k = 0; k < CNT; k++)
+                __stcs(base + (size_t)(off + k) * ld + i, r[k]);
+        }
+    }
+
+    template <int D>
+    __device__ __forceinline__ void flush(double *__restrict__ /*base*/) const {}
+};
+
+template <>
+struct TileIO<LAYOUT_AOS>
+{
+    size_t i;     // this thread's instance
+    size_t i0;    // first instance of this warp's 32-record span
+    int nvalid;   // records of the span that exist (0..32)
+    int lane;
+    bool valid;
+    double *ws;   // this warp's staging tile: 32 records, stride (max_width | 1) doubles
+
+    static constexpr size_t smem_bytes(int block, int max_width)
+    {
+        return (size_t)(block / 32) * 32 * (size_t)(max_width | 1) * sizeof(double);
+    }
+
+    __device__ __forceinline__ TileIO(size_t tile_base, size_t n, size_t /*ld*/, double *smem, int max_width)
+    {
+        lane = threadIdx.x & 31;
+        const int warp = threadIdx.x >> 5;
+        i0 = tile_base + (size_t)warp * 32;
+        i = i0 + lane;
+        valid = i < n;
+        const size_t left = i0 < n ? n - i0 : 0;
+        nvalid = left < 32 ? (int)left : 32;
+        ws = smem + (size_t)warp * 32 * (max_width | 1);
+    }
+
+    template <int D>
+    __device__ __forceinline__ void load(const double *__restrict__ base, double (&r)[D]) const
+    {
+        constexpr int DP = D | 1;
+        const double *src = base + i0 * D;
+        const int total = nvalid * D;
+        // coalesced: lane l reads doubles l, l+32, ... of the warp's contiguous span
+#pragma unroll
+        for (int m = 0; m < D; m++)
+        {
+            const int j = lane + 32 * m;
+            if (j < total)
+            {
+                const int rec = j / D;
+                ws[rec * DP + (j - rec * D)] = __ldcs(src + j);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < D; k++)
+            r[k] = valid ? ws[lane * DP + k] : 0.0;
+        __syncwarp();
+    }
+
+    template <int D, int CNT>
+    __device__ __forceinline__ void put(double *__restrict__ /*base*/, int off, const double (&r)[CNT]) const
+    {
+        constexpr int DP = D | 1;
+#pragma unroll
+        for (int k = 0; k < CNT; k++)
+            ws[lane * DP + off + k] = r[k];
+    }
+
+    template <int D>
+    __device__ __forceinline__ void store(double *__restrict__ base, const double (&r)[D]) const
+    {
+        put<D, D>(base, 0, r);
+        flush<D>(base);
+    }
+
+    template <int D>
+    __device__ __forceinline__ void flush(double *__restrict__ base) const
+    {
+        constexpr int DP = D | 1;
+        __syncwarp();
+        double *dst = base + i0 * D;
+        const int total = nvalid * D;
+#pragma unroll
+        for (int m = 0; m < D; m++)
+        {
+            const int j = lane + 32 * m;
+            if (j < total)
+            {
+                const int rec = j / D;
+                __stcs(dst + j, ws[rec * DP + (j - rec * D)]);
+            }
+        }
+        __syncwarp();
+    }
+};
+
+} // namespace ppx_dev

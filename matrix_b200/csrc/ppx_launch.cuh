@@ -1,0 +1,120 @@
+// ppx_launch.cuh -- one kernel skeleton and one host launcher shared by every batch_* entry point.
+//
+// An "Op" is a trivially copyable functor holding the call's pointers and per-call constants; it is
+// passed to the kernel as a __grid_constant__ parameter, i.e. it lives in the constant bank.  The
+// kernel walks the batch in tiles of Op::BLOCK consecutive instances, one instance per thread, with
+// a grid sized to a whole number of resident waves (148 SMs x blocks/SM on B200).
+#pragma once
+
+#include <atomic>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/ppx_cuda.h"
+#include "ppx_io.cuh"
+#include "ppx_math.cuh"
+
+extern std::atomic<uint64_t> g_ppx_launch_count; // util.cu
+
+#define PPX_CHECK_PTRS(...)                          \
+    do                                               \
+    {                                                \
+        const void *ptrs_[] = {__VA_ARGS__};         \
+        for (const void *p_ : ptrs_)                 \
+            if (p_ == nullptr)                       \
+                return PPX_ERR_BAD_ARGUMENT;         \
+    } while (0)
+
+
+namespace ppx_dev
+{
+
+template <int LAYOUT, class Op>
+__global__ void __launch_bounds__(Op::BLOCK, Op::MINB) batch_kernel(const __grid_constant__ Op op, size_t n, size_t ld)
+{
+    extern __shared__ __align__(16) double ppx_smem[];
+    const size_t stride = (size_t)gridDim.x * Op::BLOCK;
+    for (size_t base = (size_t)blockIdx.x * Op::BLOCK; base < n; base += stride)
+    {
+        TileIO<LAYOUT> io(base, n, ld, ppx_smem, Op::MAXW);
+        op(io);
+    }
+}
+
+struct DeviceInfo
+{
+    int sms = 0;
+};
+
+inline int device_info(DeviceInfo &info, int &device)
+{
+    static DeviceInfo cache[64];
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess)
+        return (int)e;
+    if (device < 0 || device >= 64)
+        return PPX_ERR_NO_DEVICE;
+    if (cache[device].sms == 0)
+    {
+        int sms = 0;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (e != cudaSuccess)
+            return (int)e;
+        cache[device].sms = sms;
+    }
+    info = cache[device];
+    return PPX_OK;
+}
+
+// Waves of resident CTAs the grid-stride loop is spread over: enough to hide the tail, few enough
+// that block scheduling stays negligible.
+constexpr int GRID_WAVES = 8;
+
+template <int LAYOUT, class Op>
+int launch(const Op &op, size_t n, size_t ld, void *stream)
+{
+    if (n == 0)
+        return PPX_OK;
+    if (LAYOUT == LAYOUT_SOA && ld < n)
+        return PPX_ERR_BAD_ARGUMENT;
+    DeviceInfo info;
+    int device = 0;
+    int rc = device_info(info, device);
+    if (rc != PPX_OK)
+        return rc;
+    auto kern = batch_kernel<LAYOUT, Op>;
+    const size_t smem = TileIO<LAYOUT>::smem_bytes(Op::BLOCK, Op::MAXW);
+    static int blocks_per_sm[64]; // per instantiation, per device
+    if (blocks_per_sm[device] == 0)
+    {
+        if (smem > 48 * 1024)
+        {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess)
+                return (int)e;
+        }
+        int b = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, Op::BLOCK, smem);
+        if (e != cudaSuccess)
+            return (int)e;
+        blocks_per_sm[device] = b > 0 ? b : 1;
+    }
+    const size_t tiles = (n + Op::BLOCK - 1) / Op::BLOCK;
+    const size_t cap = (size_t)info.sms * blocks_per_sm[device] * GRID_WAVES;
+    const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+    kern<<<grid, Op::BLOCK, smem, (cudaStream_t)stream>>>(op, n, ld);
+    g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaPeekAtLastError();
+}
+
+template <class Op>
+int dispatch(int layout, const Op &op, size_t n, size_t ld, void *stream)
+{
+    if (layout == PPX_LAYOUT_AOS)
+        return launch<LAYOUT_AOS>(op, n, ld, stream);
+    if (layout == PPX_LAYOUT_SOA)
+        return launch<LAYOUT_SOA>(op, n, ld, stream);
+    return PPX_ERR_BAD_LAYOUT;
+}
+
+} // namespace ppx_dev

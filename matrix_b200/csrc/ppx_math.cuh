@@ -1,0 +1,730 @@
+// ppx_math.cuh -- per-instance fp64 device math for the ppx hot path (sm_100a).
+//
+// One instance lives entirely in the registers of one thread: every array below has
+// compile-time extents and every loop is fully unrolled, so nothing is indexed dynamically
+// and nothing spills to local memory.  Semantics follow the reference routine cited beside
+// each function (file:line under the reference tree); the arithmetic is re-derived for the
+// GPU (closed forms instead of 4x4 matrix powers, reciprocals shared between coefficients,
+// rotation-aware products) and agrees with the reference to fp64 rounding, which the parity
+// tests bound at 1e-12 relative.  Branch thresholds are the reference's, exactly.
+#pragma once
+
+#include <cfloat>
+#include <cmath>
+
+namespace ppx_dev
+{
+
+constexpr double EPS_SP = 1.1920928955078125e-07; // float epsilon, include/exprtmpl.hpp:12
+constexpr double EPS_DP = 2.220446049250313e-16;  // double epsilon, include/exprtmpl.hpp:13
+constexpr double PI = 3.141592653589793;          // include/exprtmpl.hpp:11
+
+#define PPX_DEV __device__ __forceinline__
+
+// Rigid transform: rotation r (column-major, r[i + 3 j]) and translation p.  An SE3 record is
+// [r0 r1 r2 0 | r3 r4 r5 0 | r6 r7 r8 0 | p0 p1 p2 1] (include/liegroup.hpp:186-200).
+struct Rigid
+{
+    double r[9];
+    double p[3];
+};
+
+PPX_DEV void rigid_identity(Rigid &t)
+{
+#pragma unroll
+    for (int i = 0; i < 9; i++)
+        t.r[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    t.p[0] = t.p[1] = t.p[2] = 0.0;
+}
+
+PPX_DEV void rigid_from_record(const double (&m)[16], Rigid &t)
+{
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            t.r[r + 3 * c] = m[r + 4 * c];
+    t.p[0] = m[12], t.p[1] = m[13], t.p[2] = m[14];
+}
+
+PPX_DEV void rigid_to_record(const Rigid &t, double (&m)[16])
+{
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+    {
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            m[r + 4 * c] = t.r[r + 3 * c];
+        m[3 + 4 * c] = 0.0;
+    }
+    m[12] = t.p[0], m[13] = t.p[1], m[14] = t.p[2], m[15] = 1.0;
+}
+
+// y = R x
+PPX_DEV void rot_apply(const double (&r)[9], const double (&x)[3], double (&y)[3])
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        y[i] = fma(r[i + 6], x[2], fma(r[i + 3], x[1], r[i] * x[0]));
+}
+
+// y = R^T x
+PPX_DEV void rot_apply_t(const double (&r)[9], const double (&x)[3], double (&y)[3])
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        y[i] = fma(r[3 * i + 2], x[2], fma(r[3 * i + 1], x[1], r[3 * i] * x[0]));
+}
+
+PPX_DEV void cross3(const double (&a)[3], const double (&b)[3], double (&c)[3])
+{
+    c[0] = fma(a[1], b[2], -a[2] * b[1]);
+    c[1] = fma(a[2], b[0], -a[0] * b[2]);
+    c[2] = fma(a[0], b[1], -a[1] * b[0]);
+}
+
+// C = A * B for rigid transforms (SE3::operator*, include/liegroup.hpp:204-207); the constant
+// bottom row of the 4x4 product is not recomputed: 27 + 9 multiply-adds instead of 64.
+PPX_DEV void rigid_mul(const Rigid &a, const Rigid &b, Rigid &c)
+{
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            c.r[i + 3 * j] = fma(a.r[i + 6], b.r[2 + 3 * j], fma(a.r[i + 3], b.r[1 + 3 * j], a.r[i] * b.r[3 * j]));
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        c.p[i] = fma(a.r[i + 6], b.p[2], fma(a.r[i + 3], b.p[1], fma(a.r[i], b.p[0], a.p[i])));
+}
+
+// SE3::I, include/liegroup.hpp:227-230: (R^T, -R^T p)
+PPX_DEV void rigid_inv(const Rigid &a, Rigid &b)
+{
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            b.r[i + 3 * j] = a.r[j + 3 * i];
+    double t[3];
+    rot_apply_t(a.r, a.p, t);
+    b.p[0] = -t[0], b.p[1] = -t[1], b.p[2] = -t[2];
+}
+
+// SE3::Adt, include/liegroup.hpp:217-226, as a dense 6x6 record (column-major, ad[r + 6 c]):
+// [[R, 0], [hat(p) R, R]].
+PPX_DEV void rigid_adjoint_record(const Rigid &t, double (&ad)[36])
+{
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+    {
+        const double col[3] = {t.r[3 * c], t.r[3 * c + 1], t.r[3 * c + 2]};
+        double pc[3];
+        cross3(t.p, col, pc);
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+        {
+            ad[r + 6 * c] = col[r];
+            ad[r + 3 + 6 * c] = pc[r];
+            ad[r + 6 * (c + 3)] = 0.0;
+            ad[r + 3 + 6 * (c + 3)] = col[r];
+        }
+    }
+}
+
+// Ad(T) * (w; v) without forming the 6x6: (R w ; p x (R w) + R v)
+PPX_DEV void rigid_adjoint_apply(const Rigid &t, const double (&w)[3], const double (&v)[3], double (&out)[6])
+{
+    double rw[3], rv[3], c[3];
+    rot_apply(t.r, w, rw);
+    rot_apply(t.r, v, rv);
+    cross3(t.p, rw, c);
+    out[0] = rw[0], out[1] = rw[1], out[2] = rw[2];
+    out[3] = c[0] + rv[0], out[4] = c[1] + rv[1], out[5] = c[2] + rv[2];
+}
+
+// so3::exp, include/liegroup.hpp:116-133 (identity below near_zero = 1e-6, include/matrixs.hpp:39-42).
+PPX_DEV void so3_exp(const double (&w)[3], double (&r)[9])
+{
+    const double t2 = fma(w[2], w[2], fma(w[1], w[1], w[0] * w[0]));
+    const double theta = sqrt(t2);
+    double s, c;
+    sincos(theta, &s, &c);
+    const bool tiny = fabs(theta) < 1.0e-6;
+    const double inv = tiny ? 0.0 : 1.0 / t2;
+    const double a = tiny ? 0.0 : s * theta * inv; // sin(theta)/theta
+    const double b = (1.0 - c) * inv;              // (1-cos(theta))/theta^2
+    // I + a W + b W^2,  W^2 = w w^T - theta^2 I,  1 - b theta^2 = cos(theta)
+    const double d = tiny ? 1.0 : c;
+    const double bw0 = b * w[0], bw1 = b * w[1], bw2 = b * w[2];
+    r[0] = fma(bw0, w[0], d);
+    r[4] = fma(bw1, w[1], d);
+    r[8] = fma(bw2, w[2], d);
+    r[1] = fma(bw0, w[1], a * w[2]);
+    r[3] = fma(bw0, w[1], -a * w[2]);
+    r[2] = fma(bw0, w[2], -a * w[1]);
+    r[6] = fma(bw0, w[2], a * w[1]);
+    r[5] = fma(bw1, w[2], a * w[0]);
+    r[7] = fma(bw1, w[2], -a * w[0]);
+}
+
+// SO3::log, include/liegroup.hpp:60-92, all three branches.
+PPX_DEV void SO3_log(const double (&r)[9], double (&w)[3])
+{
+    const double acosinput = ((r[0] + r[4]) + r[8] - 1.0) * 0.5;
+    if (acosinput >= 1.0)
+    {
+        w[0] = w[1] = w[2] = 0.0;
+    }
+    else if (acosinput <= -1.0)
+    {
+        double s, v0, v1, v2;
+        if (!(fabs(1.0 + r[8]) < EPS_SP))
+        {
+            s = 1.0 / sqrt(2.0 + 2.0 * r[8]);
+            v0 = r[6], v1 = r[7], v2 = 1.0 + r[8];
+        }
+        else if (!(fabs(1.0 + r[4]) < EPS_SP))
+        {
+            s = 1.0 / sqrt(2.0 + 2.0 * r[4]);
+            v0 = r[3], v1 = 1.0 + r[4], v2 = r[5];
+        }
+        else
+        {
+            s = 1.0 / sqrt(2.0 + 2.0 * r[0]);
+            v0 = 1.0 + r[0], v1 = r[1], v2 = r[2];
+        }
+        w[0] = PI * (s * v0), w[1] = PI * (s * v1), w[2] = PI * (s * v2);
+    }
+    else
+    {
+        const double theta = acos(acosinput);
+        // sin(acos(c)) = sqrt((1-c)(1+c)): one sqrt instead of a second transcendental
+        const double st = sqrt((1.0 - acosinput) * (1.0 + acosinput));
+        const double k = theta / (2.0 * st);
+        w[0] = (r[5] - r[7]) * k;
+        w[1] = (r[6] - r[2]) * k;
+        w[2] = (r[1] - r[3]) * k;
+    }
+}
+
+// se3::exp, include/liegroup.hpp:253-269.  Closed form of I + X + c1 X^2 + c2 X^3 for X = hat(xi):
+//   R = cos(phi) I + (sin(phi)/phi) W + c1 w w^T,   p = v + c1 (w x v) + c2 (w x (w x v)),
+// with c1 = (1-cos phi)/phi^2, c2 = (phi - sin phi)/phi^3; R = I, p = v when |phi| < EPS_SP (:258-261).
+PPX_DEV void se3_exp(const double (&xi)[6], Rigid &t)
+{
+    const double w[3] = {xi[0], xi[1], xi[2]};
+    const double v[3] = {xi[3], xi[4], xi[5]};
+    const double p2 = fma(w[2], w[2], fma(w[1], w[1], w[0] * w[0]));
+    const double phi = sqrt(p2);
+    const bool tiny = fabs(phi) < EPS_SP;
+    double s, c;
+    sincos(phi, &s, &c);
+    const double inv = tiny ? 0.0 : 1.0 / p2;
+    const double iphi = phi * inv;        // 1/phi
+    const double a = tiny ? 0.0 : s * iphi;
+    const double c1 = (1.0 - c) * inv;
+    const double c2 = (phi - s) * inv * iphi;
+    const double d = tiny ? 1.0 : c;
+    const double bw0 = c1 * w[0], bw1 = c1 * w[1], bw2 = c1 * w[2];
+    t.r[0] = fma(bw0, w[0], d);
+    t.r[4] = fma(bw1, w[1], d);
+    t.r[8] = fma(bw2, w[2], d);
+    t.r[1] = fma(bw0, w[1], a * w[2]);
+    t.r[3] = fma(bw0, w[1], -a * w[2]);
+    t.r[2] = fma(bw0, w[2], -a * w[1]);
+    t.r[6] = fma(bw0, w[2], a * w[1]);
+    t.r[5] = fma(bw1, w[2], a * w[0]);
+    t.r[7] = fma(bw1, w[2], -a * w[0]);
+    double wv[3], wwv[3];
+    cross3(w, v, wv);
+    cross3(w, wv, wwv);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        t.p[i] = fma(c2, wwv[i], fma(c1, wv[i], v[i]));
+}
+
+// SE3::log, include/liegroup.hpp:231-250.  Generic branch only while |ctheta| < 1; otherwise
+// (theta = 0 and, as in the reference, also theta = pi) the result is (0, p).
+//   theta = acos(c), sin(theta) = sqrt((1-c)(1+c)), 1/(2 tan(theta/2)) = (1+c)/(2 sin(theta))
+//   w = vee(R - R^T) theta / (2 sin theta),  v = p - (w x p)/2 + coff1 (w x (w x p))
+PPX_DEV void SE3_log(const Rigid &t, double (&xi)[6])
+{
+    const double ct = ((t.r[0] + t.r[4]) + t.r[8] - 1.0) * 0.5;
+    if (fabs(ct) < 1.0)
+    {
+        const double theta = acos(ct);
+        const double st = sqrt((1.0 - ct) * (1.0 + ct));
+        const double ist = 1.0 / (2.0 * st);
+        const double ith = 1.0 / theta;
+        const double k = theta * ist;
+        const double coff1 = (ith - (1.0 + ct) * ist) * ith;
+        const double w[3] = {(t.r[5] - t.r[7]) * k, (t.r[6] - t.r[2]) * k, (t.r[1] - t.r[3]) * k};
+        double wp[3], wwp[3];
+        cross3(w, t.p, wp);
+        cross3(w, wp, wwp);
+        xi[0] = w[0], xi[1] = w[1], xi[2] = w[2];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            xi[3 + i] = fma(coff1, wwp[i], fma(-0.5, wp[i], t.p[i]));
+    }
+    else
+    {
+        xi[0] = xi[1] = xi[2] = 0.0;
+        xi[3] = t.p[0], xi[4] = t.p[1], xi[5] = t.p[2];
+    }
+}
+
+// se3::adt, include/liegroup.hpp:271-280: [[hat(w), 0], [hat(v), hat(w)]] as a dense 6x6 record.
+PPX_DEV void se3_adt_record(const double (&xi)[6], double (&ad)[36])
+{
+#pragma unroll
+    for (int i = 0; i < 36; i++)
+        ad[i] = 0.0;
+    const double w0 = xi[0], w1 = xi[1], w2 = xi[2], v0 = xi[3], v1 = xi[4], v2 = xi[5];
+    // hat(x) = [0 -x2 x1; x2 0 -x0; -x1 x0 0]
+    ad[1 + 6 * 0] = w2, ad[2 + 6 * 0] = -w1, ad[0 + 6 * 1] = -w2, ad[2 + 6 * 1] = w0, ad[0 + 6 * 2] = w1, ad[1 + 6 * 2] = -w0;
+    ad[4 + 6 * 0] = v2, ad[5 + 6 * 0] = -v1, ad[3 + 6 * 1] = -v2, ad[5 + 6 * 1] = v0, ad[3 + 6 * 2] = v1, ad[4 + 6 * 2] = -v0;
+    ad[4 + 6 * 3] = w2, ad[5 + 6 * 3] = -w1, ad[3 + 6 * 4] = -w2, ad[5 + 6 * 4] = w0, ad[3 + 6 * 5] = w1, ad[4 + 6 * 5] = -w0;
+}
+
+// so3 ljac / ljacinv / rjac / rjacinv, include/liegroup.hpp:142-184 (which: 0..3).
+//   ljac    = I + c1 X + c2 X^2         c1 = (1-cos x)/x^2, c2 = (x - sin x)/x^3
+//   ljacinv = I - X/2 + c X^2           c  = 1/x^2 - (1+cos x)/(2 x sin x)
+// with X = hat(w), X^2 = w w^T - x^2 I; below x^2 < EPS_DP the reference keeps I +- X/2.
+PPX_DEV void so3_jac(int which, const double (&w)[3], double (&J)[9])
+{
+    const double x2 = fma(w[2], w[2], fma(w[1], w[1], w[0] * w[0]));
+    const bool inv = which & 1;
+    double lin, quad;
+    if (x2 < EPS_DP)
+    {
+        lin = inv ? -0.5 : 0.5;
+        quad = 0.0;
+    }
+    else
+    {
+        const double x = sqrt(x2);
+        double s, c;
+        sincos(x, &s, &c);
+        if (!inv)
+        {
+            lin = (1.0 - c) / x2;
+            quad = (x - s) / (x2 * x);
+        }
+        else
+        {
+            lin = -0.5;
+            quad = 1.0 / x2 - (1.0 + c) / (2.0 * x * s);
+        }
+    }
+    const double d = fma(-quad, x2, 1.0);
+    double m[9];
+    m[0] = fma(quad * w[0], w[0], d);
+    m[4] = fma(quad * w[1], w[1], d);
+    m[8] = fma(quad * w[2], w[2], d);
+    m[1] = fma(quad * w[0], w[1], lin * w[2]);
+    m[3] = fma(quad * w[0], w[1], -lin * w[2]);
+    m[2] = fma(quad * w[0], w[2], -lin * w[1]);
+    m[6] = fma(quad * w[0], w[2], lin * w[1]);
+    m[5] = fma(quad * w[1], w[2], lin * w[0]);
+    m[7] = fma(quad * w[1], w[2], -lin * w[0]);
+    if (which >= 2) // rjac = ljac^T, rjacinv = ljacinv^T
+    {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+                J[i + 3 * j] = m[j + 3 * i];
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < 9; i++)
+            J[i] = m[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Product-of-exponentials chain (demo/robotics.hpp).  The screws are the same for every instance,
+// so everything that depends on them alone is prepared once per call on the host and handed to the
+// kernel as a __grid_constant__ parameter: the compiler reads it from the constant bank as an FMA
+// operand, it costs no registers and no per-thread arithmetic.
+struct JointConst
+{
+    double w[3];    // omega
+    double v[3];    // v
+    double wv[3];   // omega x v
+    double wwv[3];  // omega x (omega x v)
+    double wn;      // |omega|
+    double iw;      // 1/|omega|       (0 when omega = 0)
+    double iw2;     // 1/|omega|^2     (0 when omega = 0)
+    double iw3;     // 1/|omega|^3     (0 when omega = 0)
+};
+
+template <int NJ>
+struct ChainConst
+{
+    JointConst joint[NJ];
+    double home_r[9];
+    double home_p[3];
+};
+
+// exp(S q) for a fixed screw S = (w; v) and a per-instance angle q (se3::exp of `JList[i].screw * q`,
+// demo/robotics.hpp:88-89).  With x = |w| q:
+//   R = I + (sin x/|w|) W + ((1-cos x)/|w|^2) W^2,  p = q v + ((1-cos x)/|w|^2) (w x v) + ((x - sin x)/|w|^3) (w x (w x v))
+// which is se3::exp's series with phi = |x|; no division and no square root per instance.
+PPX_DEV void screw_exp(const JointConst &j, double q, Rigid &t)
+{
+    const double x = j.wn * q;
+    double s, c;
+    sincos(x, &s, &c);
+    const bool tiny = fabs(x) < EPS_SP; // liegroup.hpp:258: R = I, p = v q
+    const double a = tiny ? 0.0 : s * j.iw;
+    const double b = tiny ? 0.0 : (1.0 - c) * j.iw2;
+    const double e = tiny ? 0.0 : (x - s) * j.iw3;
+    // W^2 = w w^T - |w|^2 I,  1 - b |w|^2 = cos(x)
+    const double d = tiny ? 1.0 : c;
+    const double bw0 = b * j.w[0], bw1 = b * j.w[1], bw2 = b * j.w[2];
+    t.r[0] = fma(bw0, j.w[0], d);
+    t.r[4] = fma(bw1, j.w[1], d);
+    t.r[8] = fma(bw2, j.w[2], d);
+    t.r[1] = fma(bw0, j.w[1], a * j.w[2]);
+    t.r[3] = fma(bw0, j.w[1], -a * j.w[2]);
+    t.r[2] = fma(bw0, j.w[2], -a * j.w[1]);
+    t.r[6] = fma(bw0, j.w[2], a * j.w[1]);
+    t.r[5] = fma(bw1, j.w[2], a * j.w[0]);
+    t.r[7] = fma(bw1, j.w[2], -a * j.w[0]);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        t.p[i] = fma(e, j.wwv[i], fma(b, j.wv[i], q * j.v[i]));
+}
+
+// forwardSpace + jacobiSpace in one pass (demo/robotics.hpp:83-106).  The prefix products
+// P_i = e^{S_0 q_0} ... e^{S_{i-1} q_{i-1}} are shared: column i of Js is Ad(P_i) S_i and the pose is
+// P_N M.  (The reference associates forwardSpace right-to-left; sharing the prefixes changes the
+// association, a 1e-16 effect.)  Each Jacobian column is handed to `emit(i, col)` as soon as it exists,
+// so a caller that streams columns out never holds the 6 x NJ matrix in registers.
+template <int NJ, bool WANT_T, bool WANT_J, class Emit>
+PPX_DEV void poe_fk_jacobian(const ChainConst<NJ> &ch, const double (&q)[NJ], Rigid &T, Emit &&emit)
+{
+    Rigid P;
+    if (WANT_J)
+    {
+        const double col[6] = {ch.joint[0].w[0], ch.joint[0].w[1], ch.joint[0].w[2],
+                               ch.joint[0].v[0], ch.joint[0].v[1], ch.joint[0].v[2]};
+        emit(0, col);
+    }
+    screw_exp(ch.joint[0], q[0], P);
+#pragma unroll
+    for (int i = 1; i < NJ; i++)
+    {
+        if (WANT_J)
+        {
+            double col[6];
+            rigid_adjoint_apply(P, ch.joint[i].w, ch.joint[i].v, col);
+            emit(i, col);
+        }
+        if (WANT_T || i < NJ - 1)
+        {
+            Rigid E, Q;
+            screw_exp(ch.joint[i], q[i], E);
+            rigid_mul(P, E, Q);
+            P = Q;
+        }
+    }
+    if (WANT_T)
+    {
+        Rigid M;
+#pragma unroll
+        for (int i = 0; i < 9; i++)
+            M.r[i] = ch.home_r[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            M.p[i] = ch.home_p[i];
+        rigid_mul(P, M, T);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// linsolve<Factorization::QR>, include/linalg.hpp:535-603, 1189-1200: Householder QR in the
+// reference's (Numerical-Recipes qrdcmp) form, least-squares solve, SINGULAR flag when a pivot
+// column has squared norm below EPS_DP; on SINGULAR x is the untouched head of b.
+template <int M, int N>
+PPX_DEV int linsolve_qr(double (&A)[M * N], double (&b)[M], double (&x)[N])
+{
+    static_assert(M >= N, "QR needs m >= n");
+    double b0[N];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        b0[i] = b[i];
+    bool singular = false;
+    double ic[N], id[N];
+#pragma unroll
+    for (int k = 0; k < N; k++)
+    {
+        double sum = 0.0;
+#pragma unroll
+        for (int i = k; i < M; i++)
+            sum = fma(A[i + k * M], A[i + k * M], sum);
+        singular |= fabs(sum) < EPS_DP;
+        const double root = sqrt(sum);
+        const double sigma = A[k + k * M] >= 0.0 ? root : -root;
+        A[k + k * M] += sigma;
+        const double c = sigma * A[k + k * M];
+        // 1/c and 1/d from one reciprocal of c*d (d = -sigma); tau is dropped when |c| <= EPS_DP (:564)
+        const double rcd = 1.0 / (c * -sigma);
+        ic[k] = fabs(c) > EPS_DP ? -sigma * rcd : 0.0;
+        id[k] = c * rcd;
+#pragma unroll
+        for (int j = k + 1; j < N; j++)
+        {
+            double tau = 0.0;
+#pragma unroll
+            for (int i = k; i < M; i++)
+                tau = fma(A[i + k * M], A[i + j * M], tau);
+            tau *= ic[k];
+#pragma unroll
+            for (int i = k; i < M; i++)
+                A[i + j * M] = fma(-tau, A[i + k * M], A[i + j * M]);
+        }
+        // apply the same reflector to b (QR::solve, :575-587)
+        double s = 0.0;
+#pragma unroll
+        for (int i = k; i < M; i++)
+            s = fma(A[i + k * M], b[i], s);
+        s *= ic[k];
+#pragma unroll
+        for (int i = k; i < M; i++)
+            b[i] = fma(-s, A[i + k * M], b[i]);
+    }
+#pragma unroll
+    for (int i = N - 1; i >= 0; i--)
+    {
+        double s = b[i];
+#pragma unroll
+        for (int j = i + 1; j < N; j++)
+            s = fma(-A[i + j * M], b[j], s);
+        b[i] = s * id[i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        x[i] = singular ? b0[i] : b[i];
+    return singular ? 3 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Jacobi rotation that annihilates the off-diagonal g of [[a, g], [g, b]]:
+// t = tan, with t = 2g / (d + sign(d) sqrt(d^2 + 4 g^2)), d = b - a;  c = 1/sqrt(1+t^2), s = t c.
+PPX_DEV void jacobi_cs(double a, double b, double g, double &c, double &s, double &t)
+{
+    const double d = b - a;
+    const double h = sqrt(fma(d, d, 4.0 * g * g));
+    const double den = d >= 0.0 ? d + h : d - h;
+    t = (g != 0.0) ? 2.0 * g / den : 0.0;
+    c = rsqrt(fma(t, t, 1.0));
+    s = t * c;
+}
+
+// One-sided (Hestenes) Jacobi SVD of an M x N matrix held column-major in registers:
+// on return A holds U diag(w) (columns = w_j u_j), w2[j] = |column j|^2, V the accumulated rotations.
+// Sweeps stop when a whole sweep (for every lane of the warp) made no rotation above the
+// fp64 threshold, so a warp never diverges inside the loop.
+template <int M, int N, bool WANT_V>
+PPX_DEV void jacobi_svd_core(double (&A)[M * N], double (&V)[N * N], double (&w2)[N])
+{
+    if (WANT_V)
+    {
+#pragma unroll
+        for (int i = 0; i < N * N; i++)
+            V[i] = (i % (N + 1) == 0) ? 1.0 : 0.0;
+    }
+    constexpr int MAX_SWEEPS = 12;
+    for (int sweep = 0; sweep < MAX_SWEEPS; sweep++)
+    {
+        bool rotated = false;
+#pragma unroll
+        for (int p = 0; p < N - 1; p++)
+#pragma unroll
+            for (int q = p + 1; q < N; q++)
+            {
+                double al = 0.0, be = 0.0, ga = 0.0;
+#pragma unroll
+                for (int i = 0; i < M; i++)
+                {
+                    al = fma(A[i + p * M], A[i + p * M], al);
+                    be = fma(A[i + q * M], A[i + q * M], be);
+                    ga = fma(A[i + p * M], A[i + q * M], ga);
+                }
+                // converged pair: |a_p . a_q| <= eps |a_p| |a_q|
+                const bool act = ga * ga > (EPS_DP * EPS_DP) * al * be;
+                rotated |= act;
+                double c, s, t;
+                jacobi_cs(al, be, ga, c, s, t);
+                c = act ? c : 1.0;
+                s = act ? s : 0.0;
+#pragma unroll
+                for (int i = 0; i < M; i++)
+                {
+                    const double x = A[i + p * M], y = A[i + q * M];
+                    A[i + p * M] = fma(c, x, -s * y);
+                    A[i + q * M] = fma(s, x, c * y);
+                }
+                if (WANT_V)
+                {
+#pragma unroll
+                    for (int i = 0; i < N; i++)
+                    {
+                        const double x = V[i + p * N], y = V[i + q * N];
+                        V[i + p * N] = fma(c, x, -s * y);
+                        V[i + q * N] = fma(s, x, c * y);
+                    }
+                }
+            }
+        if (!__any_sync(0xffffffffu, rotated))
+            break;
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++)
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; i++)
+            s = fma(A[i + j * M], A[i + j * M], s);
+        w2[j] = s;
+    }
+}
+
+// Truncated pseudo-inverse solve from the one-sided Jacobi factors (SVD::solve, linalg.hpp:886-913):
+// x = sum_j v_j (a_j . b) / w_j^2 over w_j > tsh = 0.5 sqrt(m+n+1) w_max EPS_DP, where a_j = w_j u_j.
+template <int M, int N>
+PPX_DEV void jacobi_svd_solve(const double (&A)[M * N], const double (&V)[N * N], const double (&w2)[N],
+                              const double (&b)[M], double (&x)[N])
+{
+    double wmax2 = w2[0];
+#pragma unroll
+    for (int j = 1; j < N; j++)
+        wmax2 = fmax(wmax2, w2[j]);
+    const double f = 0.5 * sqrt((double)(M + N + 1)) * EPS_DP;
+    const double tsh2 = f * f * wmax2;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        x[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; j++)
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; i++)
+            s = fma(A[i + j * M], b[i], s);
+        const double coef = w2[j] > tsh2 ? s / w2[j] : 0.0;
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            x[i] = fma(V[i + j * N], coef, x[i]);
+    }
+}
+
+// Cyclic Jacobi eigensolver for a symmetric N x N matrix (EigenValue<n>, include/linalg.hpp:967-1167:
+// same result as tred2 + implicit QL up to rounding and eigenvector sign).  S is read through its
+// lower triangle like the reference's tred2 (z(i,k), k <= i).  d = eigenvalues, Z = eigenvectors in
+// columns; `sorted` reproduces eigsrt's ascending order (:1137-1151).
+// index of the (i, j) entry of a symmetric matrix kept as its upper triangle in a dense N*N array
+__host__ __device__ constexpr int sym_ix(int i, int j, int n) { return i <= j ? i + j * n : j + i * n; }
+
+template <int N, bool WANT_Z>
+PPX_DEV void jacobi_eig_sym(const double (&S)[N * N], bool sorted, double (&d)[N], double (&Z)[N * N])
+{
+    double a[N * N]; // only the entries sym_ix() maps to are live
+    double fro2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < N; c++)
+#pragma unroll
+        for (int r = c; r < N; r++)
+        {
+            const double v = S[r + c * N]; // lower triangle, as tred2 reads it
+            a[sym_ix(r, c, N)] = v;
+            fro2 = fma(r == c ? v : 2.0 * v, v, fro2);
+        }
+    if (WANT_Z)
+    {
+#pragma unroll
+        for (int i = 0; i < N * N; i++)
+            Z[i] = (i % (N + 1) == 0) ? 1.0 : 0.0;
+    }
+    // an off-diagonal is negligible once g^2 <= (eps/N)^2 |S|_F^2: the eigenvalues then carry an
+    // absolute error of a few eps |S|_2, the same guarantee the reference's QL iteration gives
+    const double thr2 = (EPS_DP / N) * (EPS_DP / N) * fro2;
+    constexpr int MAX_SWEEPS = 12;
+    for (int sweep = 0; sweep < MAX_SWEEPS; sweep++)
+    {
+        bool rotated = false;
+#pragma unroll
+        for (int p = 0; p < N - 1; p++)
+#pragma unroll
+            for (int q = p + 1; q < N; q++)
+            {
+                const double g = a[sym_ix(p, q, N)];
+                const double app = a[sym_ix(p, p, N)], aqq = a[sym_ix(q, q, N)];
+                const bool act = g * g > thr2;
+                rotated |= act;
+                double c, s, t;
+                jacobi_cs(app, aqq, g, c, s, t);
+                c = act ? c : 1.0;
+                s = act ? s : 0.0;
+                t = act ? t : 0.0;
+                a[sym_ix(p, p, N)] = fma(-t, g, app);
+                a[sym_ix(q, q, N)] = fma(t, g, aqq);
+                a[sym_ix(p, q, N)] = act ? 0.0 : g;
+#pragma unroll
+                for (int r = 0; r < N; r++)
+                {
+                    if (r != p && r != q)
+                    {
+                        const double x = a[sym_ix(r, p, N)], y = a[sym_ix(r, q, N)];
+                        a[sym_ix(r, p, N)] = fma(c, x, -s * y);
+                        a[sym_ix(r, q, N)] = fma(s, x, c * y);
+                    }
+                }
+                if (WANT_Z)
+                {
+#pragma unroll
+                    for (int r = 0; r < N; r++)
+                    {
+                        const double x = Z[r + p * N], y = Z[r + q * N];
+                        Z[r + p * N] = fma(c, x, -s * y);
+                        Z[r + q * N] = fma(s, x, c * y);
+                    }
+                }
+            }
+        if (!__any_sync(0xffffffffu, rotated))
+            break;
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        d[i] = a[i + i * N];
+    if (sorted)
+    {
+        // ascending selection sort with compile-time indices (eigsrt swaps whole columns)
+#pragma unroll
+        for (int i = 0; i < N - 1; i++)
+#pragma unroll
+            for (int j = i + 1; j < N; j++)
+            {
+                const bool sw = d[j] < d[i];
+                const double di = d[i], dj = d[j];
+                d[i] = sw ? dj : di;
+                d[j] = sw ? di : dj;
+                if (WANT_Z)
+                {
+#pragma unroll
+                    for (int r = 0; r < N; r++)
+                    {
+                        const double x = Z[r + i * N], y = Z[r + j * N];
+                        Z[r + i * N] = sw ? y : x;
+                        Z[r + j * N] = sw ? x : y;
+                    }
+                }
+            }
+    }
+}
+
+} // namespace ppx_dev

@@ -1,0 +1,206 @@
+// solvers.cu -- batched least-squares QR, SVD / pseudo-inverse solve and symmetric eigensolver
+// (include/linalg.hpp of the reference: QR<m,n> :535-603, SVD<m,n> :605-924, EigenValue<n> :967-1167,
+// linsolve<> :1169-1209), one instance per thread, everything in registers.
+//
+// QR follows the reference's Householder recurrence step for step (fully unrolled).  SVD and eig do
+// NOT port the reference's Golub-Kahan-Reinsch / tred2+QL iterations -- their data-dependent deflation
+// logic and dynamically indexed work arrays would put a 6x6 problem in local memory and diverge inside
+// every warp.  They use cyclic Jacobi rotations instead: fixed, fully unrolled rotation schedules on
+// register-resident matrices, sweeps terminated by a warp vote.  The factors agree with the reference's
+// up to the order/sign freedom of the decomposition; singular values, eigenvalues, reconstruction and
+// every solve agree to fp64 rounding (parity tests: tests/test_gpu_parity.py).
+#include "ppx_launch.cuh"
+
+using namespace ppx_dev;
+
+namespace
+{
+
+// BASELINE config 3 at (4,3): 128 B in, 24 B + 1 B out, ~250 fp64 instructions: HBM-bound.
+template <int M, int N>
+struct OpLinsolveQR
+{
+    static constexpr int BLOCK = 128, MINB = (M * N <= 16 ? 4 : 2), MAXW = M * N;
+    const double *A;
+    const double *b;
+    double *x;
+    int8_t *status;
+    template <class IO>
+    __device__ __forceinline__ void operator()(const IO &io) const
+    {
+        double a[M * N], rhs[M], sol[N];
+        io.load(A, a);
+        io.load(b, rhs);
+        const int st = linsolve_qr<M, N>(a, rhs, sol);
+        io.store(x, sol);
+        if (status != nullptr && io.valid)
+            status[io.i] = (int8_t)st;
+    }
+};
+
+// BASELINE config 4a at (6,6): 288 B in, 624 B out, ~9k fp64 instructions: fp64-bound.
+template <int M, int N, bool WANT_U, bool WANT_V>
+struct OpSVD
+{
+    static constexpr int BLOCK = 128, MINB = 1, MAXW = (M * N > N * N ? M * N : N * N);
+    const double *A;
+    double *U;
+    double *w;
+    double *V;
+    template <class IO>
+    __device__ __forceinline__ void operator()(const IO &io) const
+    {
+        double a[M * N], v[N * N], w2[N], sv[N];
+        io.load(A, a);
+        jacobi_svd_core<M, N, WANT_V>(a, v, w2);
+#pragma unroll
+        for (int j = 0; j < N; j++)
+        {
+            sv[j] = sqrt(w2[j]);
+            if (WANT_U)
+            {
+                const double inv = sv[j] > 0.0 ? 1.0 / sv[j] : 0.0;
+#pragma unroll
+                for (int i = 0; i < M; i++)
+                    a[i + j * M] *= inv;
+            }
+        }
+        if (WANT_U)
+            io.store(U, a);
+        io.store(w, sv);
+        if (WANT_V)
+            io.store(V, v);
+    }
+};
+
+template <int M, int N>
+struct OpLinsolveSVD
+{
+    static constexpr int BLOCK = 128, MINB = 1, MAXW = M * N;
+    const double *A;
+    const double *b;
+    double *x;
+    template <class IO>
+    __device__ __forceinline__ void operator()(const IO &io) const
+    {
+        double a[M * N], v[N * N], w2[N], rhs[M], sol[N];
+        io.load(A, a);
+        io.load(b, rhs);
+        jacobi_svd_core<M, N, true>(a, v, w2);
+        jacobi_svd_solve<M, N>(a, v, w2, rhs, sol);
+        io.store(x, sol);
+    }
+};
+
+// BASELINE config 4b at n = 4: 128 B in, 160 B out, ~2k fp64 instructions.
+template <int N, bool WANT_Z>
+struct OpEigSym
+{
+    static constexpr int BLOCK = 128, MINB = (N <= 4 ? 3 : 1), MAXW = N * N;
+    const double *S;
+    double *d;
+    double *z;
+    int sorted;
+    template <class IO>
+    __device__ __forceinline__ void operator()(const IO &io) const
+    {
+        double s[N * N], ev[N], vec[N * N];
+        io.load(S, s);
+        jacobi_eig_sym<N, WANT_Z>(s, sorted != 0, ev, vec);
+        io.store(d, ev);
+        if (WANT_Z)
+            io.store(z, vec);
+    }
+};
+
+template <int M, int N>
+int svd_mn(const double *A, double *U, double *w, double *V, size_t count, int layout, size_t ld, void *stream)
+{
+    if (U && V)
+        return dispatch(layout, OpSVD<M, N, true, true>{A, U, w, V}, count, ld, stream);
+    if (U)
+        return dispatch(layout, OpSVD<M, N, true, false>{A, U, w, nullptr}, count, ld, stream);
+    if (V)
+        return dispatch(layout, OpSVD<M, N, false, true>{A, nullptr, w, V}, count, ld, stream);
+    return dispatch(layout, OpSVD<M, N, false, false>{A, nullptr, w, nullptr}, count, ld, stream);
+}
+
+template <int N>
+int eig_n(const double *S, double *d, double *z, int sorted, size_t count, int layout, size_t ld, void *stream)
+{
+    if (z)
+        return dispatch(layout, OpEigSym<N, true>{S, d, z, sorted}, count, ld, stream);
+    return dispatch(layout, OpEigSym<N, false>{S, d, nullptr, sorted}, count, ld, stream);
+}
+
+} // namespace
+
+#define PPX_SHAPE2(M_, N_, call) \
+    if (m == M_ && n == N_)      \
+    return call
+
+extern "C"
+{
+
+int ppx_cuda_batch_linsolve_qr(int m, int n, const double *A, const double *b, double *x, int8_t *status,
+                               size_t count, int layout, size_t ld, void *stream)
+{
+    if (count == 0)
+        return PPX_OK;
+    PPX_CHECK_PTRS(A, b, x);
+    PPX_SHAPE2(4, 3, dispatch(layout, OpLinsolveQR<4, 3>{A, b, x, status}, count, ld, stream));
+    PPX_SHAPE2(3, 3, dispatch(layout, OpLinsolveQR<3, 3>{A, b, x, status}, count, ld, stream));
+    PPX_SHAPE2(4, 4, dispatch(layout, OpLinsolveQR<4, 4>{A, b, x, status}, count, ld, stream));
+    PPX_SHAPE2(6, 4, dispatch(layout, OpLinsolveQR<6, 4>{A, b, x, status}, count, ld, stream));
+    PPX_SHAPE2(6, 6, dispatch(layout, OpLinsolveQR<6, 6>{A, b, x, status}, count, ld, stream));
+    return PPX_ERR_BAD_SHAPE;
+}
+
+int ppx_cuda_batch_svd(int m, int n, const double *A, double *U, double *w, double *V, size_t count, int layout,
+                       size_t ld, void *stream)
+{
+    if (count == 0)
+        return PPX_OK;
+    PPX_CHECK_PTRS(A, w);
+    PPX_SHAPE2(6, 6, (svd_mn<6, 6>(A, U, w, V, count, layout, ld, stream)));
+    PPX_SHAPE2(4, 3, (svd_mn<4, 3>(A, U, w, V, count, layout, ld, stream)));
+    PPX_SHAPE2(3, 3, (svd_mn<3, 3>(A, U, w, V, count, layout, ld, stream)));
+    PPX_SHAPE2(4, 4, (svd_mn<4, 4>(A, U, w, V, count, layout, ld, stream)));
+    PPX_SHAPE2(5, 4, (svd_mn<5, 4>(A, U, w, V, count, layout, ld, stream)));
+    PPX_SHAPE2(6, 4, (svd_mn<6, 4>(A, U, w, V, count, layout, ld, stream)));
+    return PPX_ERR_BAD_SHAPE;
+}
+
+int ppx_cuda_batch_linsolve_svd(int m, int n, const double *A, const double *b, double *x, size_t count,
+                                int layout, size_t ld, void *stream)
+{
+    if (count == 0)
+        return PPX_OK;
+    PPX_CHECK_PTRS(A, b, x);
+    PPX_SHAPE2(6, 6, dispatch(layout, OpLinsolveSVD<6, 6>{A, b, x}, count, ld, stream));
+    PPX_SHAPE2(4, 3, dispatch(layout, OpLinsolveSVD<4, 3>{A, b, x}, count, ld, stream));
+    PPX_SHAPE2(3, 3, dispatch(layout, OpLinsolveSVD<3, 3>{A, b, x}, count, ld, stream));
+    PPX_SHAPE2(4, 4, dispatch(layout, OpLinsolveSVD<4, 4>{A, b, x}, count, ld, stream));
+    PPX_SHAPE2(5, 4, dispatch(layout, OpLinsolveSVD<5, 4>{A, b, x}, count, ld, stream));
+    PPX_SHAPE2(6, 4, dispatch(layout, OpLinsolveSVD<6, 4>{A, b, x}, count, ld, stream));
+    return PPX_ERR_BAD_SHAPE;
+}
+
+int ppx_cuda_batch_eig_sym(int n, const double *S, double *d, double *z, int sorted, size_t count, int layout,
+                           size_t ld, void *stream)
+{
+    if (count == 0)
+        return PPX_OK;
+    PPX_CHECK_PTRS(S, d);
+    switch (n)
+    {
+    case 2: return eig_n<2>(S, d, z, sorted, count, layout, ld, stream);
+    case 3: return eig_n<3>(S, d, z, sorted, count, layout, ld, stream);
+    case 4: return eig_n<4>(S, d, z, sorted, count, layout, ld, stream);
+    case 5: return eig_n<5>(S, d, z, sorted, count, layout, ld, stream);
+    case 6: return eig_n<6>(S, d, z, sorted, count, layout, ld, stream);
+    }
+    return PPX_ERR_BAD_SHAPE;
+}
+
+} // extern "C"

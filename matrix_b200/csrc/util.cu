@@ -1,0 +1,194 @@
+// util.cu -- device/memory helpers behind the C ABI, layout conversion, the counter-based input
+// generator and the fp64 peak probe.  None of this is on the timed hot path.
+#include <cstdio>
+#include <cstring>
+
+#include "ppx_launch.cuh"
+
+std::atomic<uint64_t> g_ppx_launch_count{0};
+
+namespace
+{
+
+// records of `width` doubles, dense AoS <-> component-major SoA; one thread per (instance, component),
+// coalesced on the SoA side, L1/L2-merged on the AoS side (a conversion utility, not a hot kernel)
+__global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict__ soa, int width, size_t n, size_t ld)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        for (int k = 0; k < width; k++)
+            soa[(size_t)k * ld + i] = aos[i * width + k];
+}
+
+__global__ void k_soa_to_aos(const double *__restrict__ soa, double *__restrict__ aos, int width, size_t n, size_t ld)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        for (int k = 0; k < width; k++)
+            aos[i * width + k] = soa[(size_t)k * ld + i];
+}
+
+// splitmix64 finaliser over the counter seed + (j+1)*GOLDEN: matrix_b200/synth.py, bit for bit
+__global__ void k_fill_uniform(double *__restrict__ out, size_t count, uint64_t seed, uint64_t first, double lo,
+                               double hi)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const double span = hi - lo;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride)
+    {
+        uint64_t z = seed + (first + j + 1) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        const double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+        out[j] = __dadd_rn(lo, __dmul_rn(span, u)); // no FMA: numpy computes lo + span*u in two roundings
+    }
+}
+
+// 8 independent DFMA chains per thread, enough resident warps to fill every fp64 pipe
+__global__ void __launch_bounds__(256) k_fp64_probe(double *sink, int iters)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; i++)
+    {
+        a0 = fma(a0, m, c), a1 = fma(a1, m, c), a2 = fma(a2, m, c), a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c), a5 = fma(a5, m, c), a6 = fma(a6, m, c), a7 = fma(a7, m, c);
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123.456)
+        sink[0] = s;
+}
+
+int grid_for(size_t n, int block)
+{
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess)
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    size_t tiles = (n + block - 1) / block;
+    size_t cap = (size_t)sms * 16;
+    return (int)(tiles < cap ? (tiles ? tiles : 1) : cap);
+}
+
+} // namespace
+
+extern "C"
+{
+
+const char *ppx_cuda_version(void) { return "ppx-b200 0.1 (sm_100a, fp64, reference ppx v1.2)"; }
+
+const char *ppx_cuda_error_string(int code)
+{
+    switch (code)
+    {
+    case PPX_OK: return "ok";
+    case PPX_ERR_BAD_LAYOUT: return "layout must be PPX_LAYOUT_AOS or PPX_LAYOUT_SOA";
+    case PPX_ERR_BAD_SHAPE: return "shape not compiled into libppx_cuda";
+    case PPX_ERR_BAD_ARGUMENT: return "bad argument (null pointer, ld < n, out-of-range parameter)";
+    case PPX_ERR_NO_DEVICE: return "no usable CUDA device";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown ppx error";
+    }
+}
+
+int ppx_cuda_device_count(void)
+{
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
+int ppx_cuda_set_device(int device) { return (int)cudaSetDevice(device); }
+int ppx_cuda_malloc(void **dptr, size_t bytes) { return (int)cudaMalloc(dptr, bytes); }
+int ppx_cuda_free(void *dptr) { return (int)cudaFree(dptr); }
+int ppx_cuda_malloc_host(void **hptr, size_t bytes) { return (int)cudaMallocHost(hptr, bytes); }
+int ppx_cuda_free_host(void *hptr) { return (int)cudaFreeHost(hptr); }
+
+int ppx_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream)
+{
+    return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+}
+
+int ppx_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream)
+{
+    return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+}
+
+int ppx_cuda_stream_synchronize(void *stream) { return (int)cudaStreamSynchronize((cudaStream_t)stream); }
+
+uint64_t ppx_cuda_launch_count(void) { return g_ppx_launch_count.load(std::memory_order_relaxed); }
+
+int ppx_cuda_aos_to_soa(const double *aos, double *soa, int width, size_t n, size_t ld, void *stream)
+{
+    if (n == 0)
+        return PPX_OK;
+    if (!aos || !soa || width < 1 || ld < n)
+        return PPX_ERR_BAD_ARGUMENT;
+    k_aos_to_soa<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(aos, soa, width, n, ld);
+    g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaPeekAtLastError();
+}
+
+int ppx_cuda_soa_to_aos(const double *soa, double *aos, int width, size_t n, size_t ld, void *stream)
+{
+    if (n == 0)
+        return PPX_OK;
+    if (!aos || !soa || width < 1 || ld < n)
+        return PPX_ERR_BAD_ARGUMENT;
+    k_soa_to_aos<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(soa, aos, width, n, ld);
+    g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaPeekAtLastError();
+}
+
+int ppx_cuda_fill_uniform(double *out, size_t count, uint64_t seed, uint64_t first, double lo, double hi,
+                          void *stream)
+{
+    if (count == 0)
+        return PPX_OK;
+    if (!out)
+        return PPX_ERR_BAD_ARGUMENT;
+    k_fill_uniform<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(out, count, seed, first, lo, hi);
+    g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaPeekAtLastError();
+}
+
+int ppx_cuda_fp64_peak_probe(double *tflops, void *stream)
+{
+    if (!tflops)
+        return PPX_ERR_BAD_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return (int)e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double *sink = nullptr;
+    if ((e = cudaMalloc(&sink, sizeof(double))) != cudaSuccess)
+        return (int)e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    const int iters = 1 << 15, blocks = sms * 8, threads = 256;
+    k_fp64_probe<<<blocks, threads, 0, s>>>(sink, 1 << 10); // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++)
+    {
+        cudaEventRecord(t0, s);
+        k_fp64_probe<<<blocks, threads, 0, s>>>(sink, iters);
+        cudaEventRecord(t1, s);
+        cudaEventSynchronize(t1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        const double flops = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks;
+        const double tf = flops / ((double)ms * 1e-3) * 1e-12;
+        if (tf > best)
+            best = tf;
+    }
+    g_ppx_launch_count.fetch_add(6, std::memory_order_relaxed);
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(sink);
+    *tflops = best;
+    return (int)cudaGetLastError();
+}
+
+} // extern "C"

@@ -1,0 +1,170 @@
+"""Host-buffer batch API: numpy arrays of dense reference records in, numpy arrays out.
+
+This is the drop-in call for code that holds std::vector<ppx::MatrixS<M,N>>-style host data: each
+function is one ppx_cuda_host_* call, which chunks the batch and overlaps H2D, kernel and D2H on three
+streams.  Use pinned_empty() for the buffers to get asynchronous copies at full PCIe rate.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by page-locked host memory (owned by a torch pinned tensor)."""
+    import torch
+    t = torch.empty(tuple(np.atleast_1d(shape)), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+    a = t.numpy()
+    _KEEP[a.__array_interface__["data"][0]] = t
+    return a
+
+
+_KEEP = {}
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _arr(a, width):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    a = a.reshape(-1, width)
+    return a
+
+
+def _outbuf(out, n, width, dtype=np.float64):
+    if out is None:
+        return np.empty((n, width) if width else (n,), dtype=dtype)
+    assert out.flags.c_contiguous and out.dtype == dtype and out.size == n * max(width, 1)
+    return out
+
+
+def _unary(fn, x, win, wout, out):
+    x = _arr(x, win)
+    y = _outbuf(out, x.shape[0], wout)
+    check(fn(_p(x), _p(y), x.shape[0]))
+    return y
+
+
+def so3_exp(w, out=None):
+    return _unary(lib.ppx_cuda_host_so3_exp, w, 3, 9, out)
+
+
+def SO3_log(R, out=None):
+    return _unary(lib.ppx_cuda_host_SO3_log, R, 9, 3, out)
+
+
+def se3_exp(xi, out=None):
+    return _unary(lib.ppx_cuda_host_se3_exp, xi, 6, 16, out)
+
+
+def SE3_log(T, out=None):
+    return _unary(lib.ppx_cuda_host_SE3_log, T, 16, 6, out)
+
+
+def se3_exp_log(xi, out=None):
+    return _unary(lib.ppx_cuda_host_se3_exp_log, xi, 6, 6, out)
+
+
+def SE3_inv(T, out=None):
+    return _unary(lib.ppx_cuda_host_SE3_inv, T, 16, 16, out)
+
+
+def SE3_Adt(T, out=None):
+    return _unary(lib.ppx_cuda_host_SE3_Adt, T, 16, 36, out)
+
+
+def se3_adt(xi, out=None):
+    return _unary(lib.ppx_cuda_host_se3_adt, xi, 6, 36, out)
+
+
+def SE3_mul(A, B, out=None):
+    A, B = _arr(A, 16), _arr(B, 16)
+    y = _outbuf(out, A.shape[0], 16)
+    check(lib.ppx_cuda_host_SE3_mul(_p(A), _p(B), _p(y), A.shape[0]))
+    return y
+
+
+def so3_jac(which, w, out=None):
+    k = {"ljac": 0, "ljacinv": 1, "rjac": 2, "rjacinv": 3}[which] if isinstance(which, str) else int(which)
+    w = _arr(w, 3)
+    y = _outbuf(out, w.shape[0], 9)
+    check(lib.ppx_cuda_host_so3_jac(k, _p(w), _p(y), w.shape[0]))
+    return y
+
+
+class Kinematics:
+    """demo/robotics.hpp's kinematics<N> on host arrays."""
+
+    def __init__(self, screws, home):
+        self.screws = np.ascontiguousarray(screws, dtype=np.float64).reshape(-1, 6)
+        self.home = np.ascontiguousarray(home, dtype=np.float64).reshape(16)
+        self.njoints = self.screws.shape[0]
+
+    def fk_jacobian(self, q, want_T=True, want_Js=True, out_T=None, out_Js=None):
+        q = _arr(q, self.njoints)
+        n = q.shape[0]
+        T = _outbuf(out_T, n, 16) if want_T else None
+        Js = _outbuf(out_Js, n, 6 * self.njoints) if want_Js else None
+        check(lib.ppx_cuda_host_poe_fk_jacobian(_p(self.screws), _p(self.home), self.njoints, _p(q), _p(T), _p(Js), n))
+        return T, Js
+
+    def forwardSpace(self, q):
+        return self.fk_jacobian(q, want_Js=False)[0]
+
+    def jacobiSpace(self, q):
+        return self.fk_jacobian(q, want_T=False)[1]
+
+    def ik_newton_step(self, q, Ttarget, want_Vs=False, out=None):
+        q, Tt = _arr(q, self.njoints), _arr(Ttarget, 16)
+        n = q.shape[0]
+        qo = _outbuf(out, n, self.njoints)
+        Vs = np.empty((n, 6)) if want_Vs else None
+        check(lib.ppx_cuda_host_ik_newton_step(_p(self.screws), _p(self.home), self.njoints, _p(q), _p(Tt), _p(qo),
+                                               _p(Vs), n))
+        return (qo, Vs) if want_Vs else qo
+
+    def inverseSpace(self, Ttarget, init, max_iter=20):
+        q, Tt = _arr(init, self.njoints), _arr(Ttarget, 16)
+        n = q.shape[0]
+        qo = np.empty((n, self.njoints))
+        iters = np.empty(n, dtype=np.int32)
+        status = np.empty(n, dtype=np.int8)
+        check(lib.ppx_cuda_host_ik_solve(_p(self.screws), _p(self.home), self.njoints, _p(q), _p(Tt), int(max_iter),
+                                         _p(qo), _p(iters), _p(status), n))
+        return qo, iters, status
+
+
+def linsolve(factorization, m, n, A, b):
+    A, b = _arr(A, m * n), _arr(b, m)
+    cnt = A.shape[0]
+    x = np.empty((cnt, n))
+    if factorization == "QR":
+        st = np.empty(cnt, dtype=np.int8)
+        check(lib.ppx_cuda_host_linsolve_qr(m, n, _p(A), _p(b), _p(x), _p(st), cnt))
+    elif factorization == "SVD":
+        st = np.zeros(cnt, dtype=np.int8)
+        check(lib.ppx_cuda_host_linsolve_svd(m, n, _p(A), _p(b), _p(x), cnt))
+    else:
+        raise ValueError("factorization must be 'QR' or 'SVD'")
+    return x, st
+
+
+def svdcmp(m, n, A, want_U=True, want_V=True):
+    A = _arr(A, m * n)
+    cnt = A.shape[0]
+    U = np.empty((cnt, m * n)) if want_U else None
+    w = np.empty((cnt, n))
+    V = np.empty((cnt, n * n)) if want_V else None
+    check(lib.ppx_cuda_host_svd(m, n, _p(A), _p(U), _p(w), _p(V), cnt))
+    return U, w, V
+
+
+def eig(n, S, sorted=True, vectors=True):
+    S = _arr(S, n * n)
+    cnt = S.shape[0]
+    d = np.empty((cnt, n))
+    z = np.empty((cnt, n * n)) if vectors else None
+    check(lib.ppx_cuda_host_eig_sym(n, _p(S), _p(d), _p(z), 1 if sorted else 0, cnt))
+    return d, z

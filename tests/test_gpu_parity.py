@@ -1,0 +1,521 @@
+"""Parity of the CUDA path with the CPU oracle (run on the B200 box: pytest -m gpu).
+
+Every test calls libppx_cuda.so through its C ABI (matrix_b200.batch / matrix_b200.host are thin
+ctypes wrappers) and compares with the C restatement of the reference (oracle/ppx_oracle.c, pinned
+bit-for-bit to the reference by tests/test_oracle.py) on identical seeded inputs, with the reference's
+golden vectors and with the reference outputs recorded in tests/golden/ref_outputs.npz.
+
+Tolerances (fp64, north_star: 1e-12 relative):
+  REL  = 1e-12  per-instance inf-norm relative error  |gpu - ref|_inf / |ref|_inf
+  solves (QR / SVD / IK step) are compared condition-aware: error <= REL * max(1, kappa(A)), because
+  the reference's own FMA and non-FMA builds already differ by ~kappa * 1e-16;
+  the fraction inside the flat 1e-12 bar is asserted separately.
+  SVD / eig: sorted singular values / eigenvalues relative to the largest, reconstruction residual,
+  orthogonality; vectors only up to sign.
+"""
+import numpy as np
+import pytest
+
+from matrix_b200 import synth
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+REL = 1e-12
+EPS = 2.220446049250313e-16
+LAYOUTS = ["aos", "soa"]
+
+
+@pytest.fixture(scope="module")
+def mb():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from matrix_b200 import batch
+    return batch
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def run(mb, fn, layout, *arrays, **kw):
+    """Call a batch function on numpy AoS inputs in the given layout; return numpy AoS outputs."""
+    lay = mb.AOS if layout == "aos" else mb.SOA
+    n = arrays[0].shape[0]
+    ins = [dev(a) if layout == "aos" else mb.to_soa(dev(a)) for a in arrays]
+    out = fn(*ins, layout=lay, **kw)
+    single = not isinstance(out, tuple)
+    outs = (out,) if single else out
+
+    def back(t):
+        if t is None:
+            return None
+        if t.dtype != torch.float64:
+            return t.cpu().numpy()
+        return (t if layout == "aos" else mb.to_aos(t, n)).cpu().numpy()
+
+    res = tuple(back(t) for t in outs)
+    torch.cuda.synchronize()
+    return res[0] if single else res
+
+
+def rel_err(a, b, floor=0.0):
+    """per-instance |a-b|_inf / max(|b|_inf, floor)"""
+    a = a.reshape(a.shape[0], -1)
+    b = b.reshape(b.shape[0], -1)
+    den = np.maximum(np.abs(b).max(axis=1), floor)
+    den = np.where(den == 0.0, 1.0, den)
+    return np.abs(a - b).max(axis=1) / den
+
+
+N = 1 << 16
+RAGGED = 1000 * 33 + 7  # not a multiple of the warp, block or tile size
+
+
+# --------------------------------------------------------------------------------------- Lie ops
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_se3_exp(mb, port, layout):
+    xi = synth.se3_twists(RAGGED)
+    T = run(mb, mb.se3_exp, layout, xi)
+    ref = port.se3_exp(xi)
+    assert rel_err(T, ref).max() < REL
+    assert np.all(T[:, [3, 7, 11]] == 0.0) and np.all(T[:, 15] == 1.0)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_SE3_log_same_inputs(mb, port, layout):
+    xi = synth.se3_twists(RAGGED)
+    T = port.se3_exp(xi)
+    got = run(mb, mb.SE3_log, layout, T)
+    assert rel_err(got, port.SE3_log(T)).max() < REL
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_se3_exp_log_fused_round_trip(mb, port, layout):
+    xi = synth.se3_twists(N)  # theta in [0.05, pi - 0.05]
+    got = run(mb, mb.se3_exp_log, layout, xi)
+    ref = port.se3_exp_log(xi)
+    assert rel_err(got, ref).max() < REL
+    assert rel_err(got, xi).max() < 1e-11  # identity, conditioned by 1/sin^2(theta)
+
+
+def test_lie_edge_cases_against_recorded_reference(mb, fixtures):
+    """theta in {0, 1e-9, 1e-7, 1.2e-7, 1e-6, 1e-3, .., pi-1e-6, pi}: every branch of exp / log."""
+    xi = fixtures["se3_exp.xi"]
+    T = run(mb, mb.se3_exp, "aos", xi)
+    assert rel_err(T, fixtures["se3_exp.T"]).max() < REL
+    # identity branch is exact (liegroup.hpp:258-261)
+    small = np.linalg.norm(xi[:, :3], axis=1) < 1.1920928955078125e-07
+    assert np.array_equal(T[small], fixtures["se3_exp.T"][small])
+    lg = run(mb, mb.SE3_log, "aos", fixtures["SE3_log.T"])
+    ref = fixtures["SE3_log.xi"]
+    Tin = fixtures["SE3_log.T"]
+    ct = (Tin[:, 0] + Tin[:, 5] + Tin[:, 10] - 1) / 2
+    # same branch as the reference everywhere, including its (0, p) result at theta = pi
+    assert np.array_equal(np.all(lg[:, :3] == 0, axis=1), np.all(ref[:, :3] == 0, axis=1))
+    # acos amplifies last-bit differences by 1/sin(theta): condition-aware bound
+    s = np.sqrt(np.maximum(1 - ct * ct, 1e-300))
+    tol = np.where(np.abs(ct) < 1, REL + 8 * EPS / np.maximum(s, 1e-8) ** 2, REL)
+    assert np.all(rel_err(lg, ref, floor=1.0) <= tol)
+    w = fixtures["so3_exp.w"]
+    assert rel_err(run(mb, mb.so3_exp, "aos", w), fixtures["so3_exp.R"]).max() < REL
+    R = fixtures["SO3_log.R"]
+    got = run(mb, mb.SO3_log, "aos", R)
+    ref = fixtures["SO3_log.w"]
+    c = (R[:, 0] + R[:, 4] + R[:, 8] - 1) / 2
+    s = np.sqrt(np.maximum(1 - c * c, 1e-300))
+    tol = np.where(np.abs(c) < 1, REL + 8 * EPS / np.maximum(s, 1e-8) ** 2, REL)
+    assert np.all(rel_err(got, ref, floor=1.0) <= tol)
+    # exact pi turns: the three sub-branches of liegroup.hpp:68-84
+    assert np.allclose(np.abs(got[1:4]), np.pi * np.eye(3), atol=1e-15)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_so3_exp_log_jac(mb, port, layout):
+    w = synth.se3_twists(N)[:, :3].copy()
+    R = run(mb, mb.so3_exp, layout, w)
+    ref = port.so3_exp(w)
+    assert rel_err(R, ref).max() < REL
+    assert rel_err(run(mb, mb.SO3_log, layout, ref), port.SO3_log(ref)).max() < REL
+    for k, name in enumerate(["ljac", "ljacinv", "rjac", "rjacinv"]):
+        lay = mb.AOS if layout == "aos" else mb.SOA
+        x = dev(w) if layout == "aos" else mb.to_soa(dev(w))
+        J = mb.so3_jac(name, x, layout=lay)
+        J = (J if layout == "aos" else mb.to_aos(J, w.shape[0])).cpu().numpy()
+        refJ = port.so3_jac(k, w)
+        # ljacinv's coefficient 1/x^2 - (1+cos x)/(2 x sin x) cancels near pi: bound by its conditioning
+        th = np.linalg.norm(w, axis=1)
+        tol = REL * np.maximum(1.0, 1.0 / np.abs(np.sin(th))) if k in (1, 3) else REL
+        assert np.all(rel_err(J, refJ, floor=1.0) <= tol), name
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_SE3_mul_inv_Adt_adt(mb, port, layout):
+    xi = synth.se3_twists(N)
+    A = port.se3_exp(xi)
+    B = port.se3_exp(synth.se3_twists(N, first=N))
+    assert rel_err(run(mb, mb.SE3_mul, layout, A, B), port.SE3_mul(A, B)).max() < REL
+    assert rel_err(run(mb, mb.SE3_inv, layout, A), port.SE3_inv(A)).max() < REL
+    assert rel_err(run(mb, mb.SE3_Adt, layout, A), port.SE3_Adt(A)).max() < REL
+    ad = run(mb, mb.se3_adt, layout, xi)
+    assert np.array_equal(ad, port.se3_adt(xi))  # pure data movement: bit-exact
+
+
+# --------------------------------------------------------------------------------------- kinematics
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_ur5_fk_jacobian(mb, port, layout):
+    kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
+    q = synth.joint_angles(RAGGED)
+    T, Js = run(mb, kin.fk_jacobian, layout, q)
+    rT, rJ = port.poe_fk_jacobian(synth.UR5_SCREWS, synth.UR5_HOME, q)
+    assert rel_err(T, rT).max() < REL
+    assert rel_err(Js, rJ).max() < REL
+    assert np.array_equal(Js[:, :6], np.broadcast_to(synth.UR5_SCREWS[0], (RAGGED, 6)))  # demo/robotics.hpp:97
+    # single-output variants give the same bits
+    assert np.array_equal(run(mb, kin.forwardSpace, layout, q), T)
+    assert np.array_equal(run(mb, kin.jacobiSpace, layout, q), Js)
+
+
+def test_fk_jacobian_recorded_reference_and_other_chains(mb, fixtures):
+    kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
+    T, Js = run(mb, kin.fk_jacobian, "aos", fixtures["ur5.q"])
+    assert rel_err(T, fixtures["ur5.T"]).max() < REL and rel_err(Js, fixtures["ur5.Js"], floor=1.0).max() < REL
+    for nj in (4, 7):  # non-unit, non-axis-aligned screws
+        k = mb.Kinematics(fixtures[f"chain{nj}.screws"], fixtures[f"chain{nj}.home"])
+        for layout in LAYOUTS:
+            T, Js = run(mb, k.fk_jacobian, layout, fixtures[f"chain{nj}.q"])
+            assert rel_err(T, fixtures[f"chain{nj}.T"]).max() < REL
+            assert rel_err(Js, fixtures[f"chain{nj}.Js"]).max() < REL
+
+
+def test_golden_ur5(mb, golden):
+    g = golden["ur5"]
+    kin = mb.Kinematics(np.array(g["screws"], dtype=float), np.array(g["home"]))
+    q = (np.array(g["q_times_pi"]) * 3.141592653589793).reshape(1, 6)
+    T, Js = run(mb, kin.fk_jacobian, "aos", q)
+    assert np.abs(T[0] - np.array(g["fk"])).max() < g["tol"]
+    assert np.abs(Js[0].reshape(6, 6)[1:] - np.array(g["jacobian_cols_1_to_5"])).max() < g["tol"]
+    # test/lie_test.cpp:211-216: Newton-SVD IK from (0,-1.5,0,0,1.5,0) reaches the target pose
+    q0 = dev(np.array(g["ik_start"]).reshape(1, 6))
+    Tt = dev(np.array(g["ik_target"]).reshape(1, 16))
+    qs, it, st = kin.inverseSpace(Tt, q0, g["ik_max_iter"])
+    Tq = kin.forwardSpace(qs).cpu().numpy()
+    assert np.abs(Tq[0] - np.array(g["ik_target"])).max() < g["tol"]
+    assert int(st[0]) == mb.CONVERGED and 1 <= int(it[0]) <= 20
+
+
+def _ik_inputs(port, n, first=0):
+    S, M = synth.UR5_SCREWS, synth.UR5_HOME
+    q = synth.joint_angles(n, first=first, seed=synth.SEEDS["ik_newton_step"])
+    Tt = port.poe_fk_jacobian(S, M, q + synth.ik_offsets(n, first=first), want_Js=False)[0]
+    Js = port.poe_fk_jacobian(S, M, q, want_T=False)[1]
+    sv = np.linalg.svd(Js.reshape(n, 6, 6), compute_uv=False)
+    return q, Tt, sv[:, 0] / sv[:, -1]
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_ik_newton_step(mb, port, layout):
+    n = 1 << 15
+    kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
+    q, Tt, kappa = _ik_inputs(port, n)
+    qo, Vs = run(mb, kin.ik_newton_step, layout, q, Tt, want_Vs=True)
+    rq, rV = port.ik_newton_step(synth.UR5_SCREWS, synth.UR5_HOME, q, Tt)
+    assert rel_err(Vs, rV).max() < REL
+    # dq = pinv(Js) Vs: forward error of the step is bounded by kappa(Js)
+    err = np.abs((qo - q) - (rq - q)).max(axis=1) / np.maximum(np.abs(rq - q).max(axis=1), 1e-300)
+    ok = kappa < 1e3  # away from UR5 singularities
+    assert ok.mean() > 0.9
+    assert np.all(err[ok] <= REL * np.maximum(1.0, kappa[ok]))
+    assert (err[ok] < REL).mean() > 0.995
+
+
+def test_ik_solve_loop(mb, port):
+    n = 1 << 13
+    kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
+    q, Tt, kappa = _ik_inputs(port, n, first=5000)
+    qs, it, st = kin.inverseSpace(dev(Tt), dev(q), 20)
+    qs, it, st = qs.cpu().numpy(), it.cpu().numpy(), st.cpu().numpy()
+    rq, rit = port.ik_solve(synth.UR5_SCREWS, synth.UR5_HOME, q, Tt, 20)
+    conv = st == mb.CONVERGED
+    assert conv.mean() > 0.99
+    # converged instances reproduce the target pose (the property lie_test.cpp:216 checks)
+    Tq = kin.forwardSpace(dev(qs)).cpu().numpy()
+    assert np.abs(Tq[conv] - Tt[conv]).max() < 1.1920928955078125e-07
+    # same number of Newton steps as the reference wherever the problem is well conditioned
+    ok = conv & (kappa < 1e2) & (rit < 20)
+    assert (it[ok] == rit[ok]).mean() > 0.98
+    same = ok & (it == rit)
+    assert np.abs(qs[same] - rq[same]).max() < 1e-9
+
+
+# --------------------------------------------------------------------------------------- solvers
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_linsolve_qr_4x3(mb, port, layout):
+    A, b = synth.lstsq_4x3(RAGGED)
+    x, st = run(mb, lambda a_, b_, layout: mb.linsolve(mb.QR, 4, 3, a_, b_, layout=layout), layout, A, b)
+    rx, rst = port.linsolve_qr(4, 3, A, b)
+    assert np.array_equal(st, rst)
+    kappa = np.linalg.cond(A.reshape(-1, 3, 4).transpose(0, 2, 1))
+    err = rel_err(x, rx)
+    assert np.all(err <= REL * np.maximum(1.0, kappa))
+    assert (err < REL).mean() > 0.999
+    # least-squares optimality: A^T (A x - b) = 0
+    Am = A.reshape(-1, 3, 4).transpose(0, 2, 1)
+    r = np.einsum("nij,nj->ni", Am, x) - b
+    g = np.einsum("nij,ni->nj", Am, r)
+    assert np.all(np.abs(g).max(axis=1) <= 1e-13 * kappa * np.maximum(1.0, np.abs(x).max(axis=1)))
+
+
+def test_linsolve_qr_singular_and_golden(mb, fixtures, golden):
+    A, b = fixtures["lstsq.A"], fixtures["lstsq.b"]
+    x, st = run(mb, lambda a_, b_, layout: mb.linsolve(mb.QR, 4, 3, a_, b_, layout=layout), "aos", A, b)
+    assert np.array_equal(st, fixtures["lstsq.status_qr"])
+    sing = st == mb.SINGULAR
+    assert sing.sum() >= 2 and np.array_equal(x[sing], b[sing][:, :3])  # untouched head of b
+    g = golden["linsolve_4x3"]
+    xg, sg = run(mb, lambda a_, b_, layout: mb.linsolve(mb.QR, 4, 3, a_, b_, layout=layout), "aos",
+                 np.array(g["A"]).reshape(1, 12), np.array(g["b"], dtype=float).reshape(1, 4))
+    assert np.abs(xg[0] - np.array(g["x"])).max() < 5e-15 and sg[0] == 0
+    xs, _ = run(mb, lambda a_, b_, layout: mb.linsolve(mb.SVD, 4, 3, a_, b_, layout=layout), "aos",
+                np.array(g["A"]).reshape(1, 12), np.array(g["b"], dtype=float).reshape(1, 4))
+    assert np.abs(xs[0] - np.array(g["x"])).max() < 5e-15
+
+
+@pytest.mark.parametrize("shape", [(3, 3), (4, 4), (6, 4), (6, 6)])
+def test_linsolve_qr_other_shapes(mb, port, shape):
+    m, n = shape
+    A = synth.dense(4096, m, n, seed=0x51 + m * 8 + n)
+    b = synth.dense(4096, m, 1, seed=0x52 + m * 8 + n)
+    x, st = run(mb, lambda a_, b_, layout: mb.linsolve(mb.QR, m, n, a_, b_, layout=layout), "soa", A, b)
+    rx, rst = port.linsolve_qr(m, n, A, b)
+    kappa = np.linalg.cond(A.reshape(-1, n, m).transpose(0, 2, 1))
+    assert np.array_equal(st, rst)
+    assert np.all(rel_err(x, rx) <= REL * np.maximum(1.0, kappa))
+
+
+def _svd_checks(A, U, w, V, m, n, rw):
+    cnt = A.shape[0]
+    Am = A.reshape(cnt, n, m).transpose(0, 2, 1)
+    Um = U.reshape(cnt, n, m).transpose(0, 2, 1)
+    Vm = V.reshape(cnt, n, n).transpose(0, 2, 1)
+    wmax = np.maximum(rw.max(axis=1), 1e-300)
+    # singular values: sorted, relative to the largest (Golub-Reinsch guarantees absolute accuracy only)
+    assert np.all(np.abs(np.sort(w, axis=1) - np.sort(rw, axis=1)).max(axis=1) / wmax < REL)
+    assert np.all(w >= 0)
+    rec = np.einsum("nij,nj,nkj->nik", Um, w, Vm)
+    nrm = np.maximum(np.abs(Am).max(axis=(1, 2)), 1e-300)
+    assert np.all(np.abs(rec - Am).max(axis=(1, 2)) / nrm < 1e-13)
+    assert np.abs(np.einsum("nji,njk->nik", Vm, Vm) - np.eye(n)).max() < 1e-13
+    full = w.min(axis=1) > 1e-8 * wmax
+    assert np.abs(np.einsum("nji,njk->nik", Um[full], Um[full]) - np.eye(n)).max() < 1e-12
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_svd_6x6(mb, port, layout):
+    n = 1 << 14
+    A = synth.dense(n, 6, 6)
+    U, w, V = run(mb, lambda a_, layout: mb.svdcmp(6, 6, a_, layout=layout), layout, A)
+    _, rw, _ = port.svd(6, 6, A)
+    _svd_checks(A, U, w, V, 6, 6, rw)
+
+
+@pytest.mark.parametrize("shape", [(4, 3), (3, 3), (4, 4), (5, 4), (6, 4)])
+def test_svd_other_shapes(mb, port, shape):
+    m, n = shape
+    A = synth.dense(4096, m, n, seed=0x61 + m * 8 + n)
+    U, w, V = run(mb, lambda a_, layout: mb.svdcmp(m, n, a_, layout=layout), "soa", A)
+    _, rw, _ = port.svd(m, n, A)
+    _svd_checks(A, U, w, V, m, n, rw)
+    # values-only call returns the same singular values
+    _, w2, _ = run(mb, lambda a_, layout: mb.svdcmp(m, n, a_, layout=layout, want_U=False, want_V=False), "soa", A)
+    assert np.abs(w2 - w).max() < 1e-14
+
+
+def test_svd_rank_deficient_edge_cases(mb, fixtures, golden):
+    A = fixtures["dense6.A"][-7:]  # zeros, identity, diag with a zero, ones, arange, triangular, Hilbert
+    U, w, V = run(mb, lambda a_, layout: mb.svdcmp(6, 6, a_, layout=layout), "aos", A)
+    rw = fixtures["dense6.w"][-7:]
+    wmax = np.maximum(rw.max(axis=1), 1e-300)
+    assert np.all(np.abs(np.sort(w, axis=1) - np.sort(rw, axis=1)).max(axis=1) / wmax < REL)
+    rec = np.einsum("nij,nj,nkj->nik", U.reshape(-1, 6, 6).transpose(0, 2, 1), w, V.reshape(-1, 6, 6).transpose(0, 2, 1))
+    assert np.abs(rec - A.reshape(-1, 6, 6).transpose(0, 2, 1)).max() < 1e-12 * 36
+    # test/matrix_test.cpp:831-835 and test/solver_test.cpp:41-104 (sigma_max to 10 eps) for the compiled shapes
+    g = golden["svd_reconstruct_4x3"]
+    Ag = np.array(g["A"], dtype=float).reshape(1, 12)
+    U, w, V = run(mb, lambda a_, layout: mb.svdcmp(4, 3, a_, layout=layout), "aos", Ag)
+    rec = U[0].reshape(3, 4).T @ np.diag(w[0]) @ V[0].reshape(3, 3)
+    assert np.abs(rec - Ag.reshape(3, 4).T).max() < g["tol"]
+    for case in golden["matrix_norm2"]["cases"]:
+        if (case["m"], case["n"]) in [(5, 4), (4, 4)]:
+            _, w, _ = run(mb, lambda a_, layout: mb.svdcmp(case["m"], case["n"], a_, layout=layout), "aos",
+                          np.array(case["A"]).reshape(1, -1))
+            assert abs(w.max() - case["norm2"]) < golden["matrix_norm2"]["tol"]
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_linsolve_svd_6x6(mb, port, layout):
+    n = 1 << 14
+    A = synth.dense(n, 6, 6)
+    b = synth.dense(n, 6, 1, seed=0xB6)
+    x, st = run(mb, lambda a_, b_, layout: mb.linsolve(mb.SVD, 6, 6, a_, b_, layout=layout), layout, A, b)
+    rx = port.linsolve_svd(6, 6, A, b)
+    kappa = np.linalg.cond(A.reshape(-1, 6, 6).transpose(0, 2, 1))
+    err = rel_err(x, rx)
+    assert np.all(err <= REL * np.maximum(1.0, kappa))
+    assert (err < REL).mean() > 0.97
+    assert np.all(st == 0)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_eig_sym_4(mb, port, layout):
+    n = 1 << 15
+    S = synth.symmetric(n, 4)
+    d, z = run(mb, lambda s_, layout: mb.eig(4, s_, sorted=True, layout=layout), layout, S)
+    rd, rz = port.eig_sym(4, S, True)
+    scale = np.abs(rd).max(axis=1)
+    assert np.all(np.abs(d - rd).max(axis=1) / scale < REL)
+    assert np.all(np.diff(d, axis=1) >= 0)  # ascending, like eigsrt (linalg.hpp:1137-1151)
+    Sm = S.reshape(n, 4, 4)  # symmetric: no transpose needed
+    Zm = z.reshape(n, 4, 4).transpose(0, 2, 1)  # [i, row, col]
+    res = np.einsum("nij,njk->nik", Sm, Zm) - Zm * d[:, None, :]
+    assert np.abs(res).max() < 1e-13 * 4
+    assert np.abs(np.einsum("nji,njk->nik", Zm, Zm) - np.eye(4)).max() < 1e-13
+    # eigenvectors agree with the reference's up to sign wherever the eigenvalue is isolated
+    Rm = rz.reshape(n, 4, 4).transpose(0, 2, 1)
+    gap = np.min(np.diff(rd, axis=1), axis=1) / scale
+    ok = gap > 1e-3
+    dots = np.abs(np.einsum("nji,nji->ni", Zm[ok], Rm[ok]))
+    assert np.abs(dots - 1).max() < 1e-10
+    # unsorted / values-only variants carry the same spectrum
+    d2, _ = run(mb, lambda s_, layout: mb.eig(4, s_, sorted=False, vectors=False, layout=layout), layout, S)
+    assert np.abs(np.sort(d2, axis=1) - d).max() < 1e-13
+
+
+def test_eig_golden_and_edge_cases(mb, fixtures, golden):
+    g = golden["eig_sym_4"]
+    d, z = run(mb, lambda s_, layout: mb.eig(4, s_, layout=layout), "aos", np.array(g["S"], dtype=float).reshape(1, 16))
+    assert np.abs(d[0] - np.array(g["d"])).max() < 1e-14
+    lit = np.array(g["z_literal"])
+    expected = np.array([-lit[c + 4 * r] for c in range(4) for r in range(4)]).reshape(4, 4)  # [col, row]
+    Z = z[0].reshape(4, 4)
+    for c in range(4):  # each eigenvector up to a global sign (the reference's own literal is "* (-1)")
+        assert min(np.abs(Z[c] - expected[c]).max(), np.abs(Z[c] + expected[c]).max()) < g["tol"]
+    S = fixtures["sym4.S"][-7:]
+    d, z = run(mb, lambda s_, layout: mb.eig(4, s_, layout=layout), "aos", S)
+    assert np.abs(d - fixtures["sym4.d_sorted"][-7:]).max() < 1e-13
+    for n in (2, 3, 5, 6):
+        Sn = synth.symmetric(2048, n, seed=0x71 + n)
+        dn, zn = run(mb, lambda s_, layout: mb.eig(n, s_, layout=layout), "soa", Sn)
+        ref = np.linalg.eigvalsh(Sn.reshape(-1, n, n))
+        assert np.abs(dn - ref).max() < 1e-13 * n
+    d6, _ = run(mb, lambda s_, layout: mb.eig(6, s_, layout=layout), "aos", fixtures["sym6.S"])
+    assert np.abs(d6 - fixtures["sym6.d_sorted"]).max() < 1e-13 * 6
+
+
+# --------------------------------------------------------------------------------------- plumbing
+def test_layouts_give_identical_bits(mb):
+    xi = synth.se3_twists(4097)
+    assert np.array_equal(run(mb, mb.se3_exp_log, "aos", xi), run(mb, mb.se3_exp_log, "soa", xi))
+    kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
+    q = synth.joint_angles(4097)
+    a, b = run(mb, kin.fk_jacobian, "aos", q), run(mb, kin.fk_jacobian, "soa", q)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 127, 129, 1025])
+def test_empty_and_ragged_batches(mb, port, n):
+    kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
+    q = synth.joint_angles(n)
+    for layout in LAYOUTS:
+        guard = torch.full((n + 64, 16), 7.0, dtype=torch.float64, device="cuda")
+        if layout == "aos":
+            T, Js = kin.fk_jacobian(dev(q).view(n, 6), layout=mb.AOS, out_T=guard[:n])
+            T = T.cpu().numpy()
+            assert torch.all(guard[n:] == 7.0)  # nothing written past the batch
+        else:
+            T, Js = run(mb, kin.fk_jacobian, layout, q)
+        if n:
+            assert rel_err(T, port.poe_fk_jacobian(synth.UR5_SCREWS, synth.UR5_HOME, q)[0]).max() < REL
+
+
+def test_soa_padding_is_untouched(mb):
+    n, ld = 1000, 1024
+    xi = synth.se3_twists(n)
+    x = torch.full((6, ld), float("nan"), dtype=torch.float64, device="cuda")
+    x[:, :n] = dev(xi).t()
+    out = torch.full((16, ld), 7.0, dtype=torch.float64, device="cuda")
+    mb.se3_exp(x, layout=mb.SOA, n=n, out=out)
+    assert torch.all(out[:, n:] == 7.0) and torch.isfinite(out[:, :n]).all()
+
+
+def test_device_generator_matches_numpy(mb):
+    t = torch.empty(100003, dtype=torch.float64, device="cuda")
+    mb.fill_uniform(t, synth.SEEDS["ur5_fk_jacobian"], 12345, -np.pi, np.pi)
+    assert np.array_equal(t.cpu().numpy(), synth.uniform(synth.SEEDS["ur5_fk_jacobian"], 12345, 100003, -np.pi, np.pi))
+
+
+def test_host_abi_matches_device_abi(mb, port):
+    from matrix_b200 import host
+    n = 300007  # several pipeline chunks for the wide outputs
+    q = host.pinned_empty((n, 6))
+    q[:] = synth.joint_angles(n)
+    kin = host.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
+    T, Js = kin.fk_jacobian(q)
+    dk = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
+    dT, dJ = dk.fk_jacobian(dev(q))
+    assert np.array_equal(T, dT.cpu().numpy()) and np.array_equal(Js, dJ.cpu().numpy())
+    xi = synth.se3_twists(50001)
+    assert np.array_equal(host.se3_exp_log(xi), mb.se3_exp_log(dev(xi)).cpu().numpy())
+    A, b = synth.lstsq_4x3(50001)
+    x, st = host.linsolve("QR", 4, 3, A, b)
+    rx, rst = port.linsolve_qr(4, 3, A, b)
+    assert np.array_equal(st, rst) and np.abs(x - rx).max() < 1e-9
+    d, z = host.eig(4, synth.symmetric(1000, 4))
+    assert np.all(np.diff(d, axis=1) >= 0)
+
+
+def test_errors_are_loud(mb):
+    from matrix_b200._lib import PpxCudaError
+    x = torch.zeros((8, 6), dtype=torch.float64, device="cuda")
+    with pytest.raises(PpxCudaError):
+        mb.linsolve(mb.QR, 7, 2, torch.zeros((8, 14), dtype=torch.float64, device="cuda"),
+                    torch.zeros((8, 7), dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        mb.se3_exp(x, layout=5)
+    with pytest.raises(TypeError):
+        mb.se3_exp(x.cpu())
+
+
+# --------------------------------------------------------------------------------------- full BASELINE sizes
+def test_full_size_properties_16M_fk_jacobian(mb):
+    """BASELINE config 2 at full size (2^24), checked through size-independent properties:
+    R orthonormal, bottom row exact, Js column 0 = S0, |omega-part of each column| = 1 (unit screws),
+    and equality with an independent second launch on a shard (bitwise)."""
+    n = 1 << 24
+    kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
+    q = torch.empty((6, n), dtype=torch.float64, device="cuda")
+    mb.fill_uniform(q, synth.SEEDS["ur5_fk_jacobian"], 0, -np.pi, np.pi)
+    T, Js = kin.fk_jacobian(q, layout=mb.SOA)
+    R = T[[0, 1, 2, 4, 5, 6, 8, 9, 10]].view(3, 3, n)  # [col, row, i]
+    G = torch.einsum("cri,dri->cdi", R, R)
+    eye = torch.eye(3, dtype=torch.float64, device="cuda")[:, :, None]
+    assert (G - eye).abs().max().item() < 1e-14
+    assert torch.all(T[[3, 7, 11]] == 0) and torch.all(T[15] == 1)
+    S0 = torch.tensor(synth.UR5_SCREWS[0], device="cuda")[:, None]
+    assert torch.all(Js[:6] == S0)
+    wn = Js.view(6, 6, n)[:, :3].norm(dim=1)
+    assert (wn - 1).abs().max().item() < 1e-14
+    lo, hi = 5_000_000, 5_065_537
+    T2, J2 = kin.fk_jacobian(q[:, lo:hi].contiguous(), layout=mb.SOA)
+    assert torch.equal(T2, T[:, lo:hi]) and torch.equal(J2, Js[:, lo:hi])
+    del T, Js, G, R
+    torch.cuda.empty_cache()
+
+
+def test_full_size_round_trip_1M(mb):
+    """BASELINE config 1 at full size: log(exp(xi)) = xi."""
+    n = 1 << 20
+    xi = dev(synth.se3_twists(n))
+    back = mb.se3_exp_log(xi)
+    err = (back - xi).abs().max(dim=1).values / xi.abs().max(dim=1).values
+    assert err.max().item() < 1e-11
