@@ -105,19 +105,9 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
-def load_cpu_oracle():
-    """-> (Oracle, kind): the compiled reference if oracle/_ref is there, else the C restatement."""
-    from oracle_lib import Oracle, available
-    if available("ref"):
-        return Oracle("ref"), "reference"
-    so = os.path.join(ROOT, "oracle", "libppx_oracle_fma.so")
-    if not os.path.exists(so):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "port"], stdout=subprocess.DEVNULL)
-    return Oracle("port_fma"), "port"
-
-
 def time_cpu(cpu_factory, sample, passes, warm=1):
     """best-of-`passes` instances/s of the CPU implementation on `sample` instances, all host threads"""
+    from bench_cpu import load_cpu_oracle
     oracle, kind = load_cpu_oracle()
     fn = cpu_factory(oracle, sample)
     for _ in range(warm):
@@ -135,10 +125,11 @@ def run_reference_arm(args, rank):
     from matrix_b200.workloads_meta import META
     if rank != 0:
         return
+    from bench_cpu import CPU, load_cpu_oracle
     meta = META[args.workload]
     sample = args.n if args.n else meta["cpu_sample"]
     oracle, kind = load_cpu_oracle()
-    fn = meta["cpu"](oracle, sample)
+    fn = CPU[args.workload](oracle, sample)
     for _ in range(args.warmup):
         fn()
     t0 = time.perf_counter()
@@ -324,8 +315,9 @@ def main():
                 except Exception as e:  # report, never hide
                     others.append({"workload": name, "error": repr(e)})
         if not args.no_cpu:
+            from bench_cpu import CPU
             meta = META[args.workload]
-            best, mean, times, kind, cores = time_cpu(meta["cpu"], meta["cpu_sample"], passes=3)
+            best, mean, times, kind, cores = time_cpu(CPU[args.workload], meta["cpu_sample"], passes=3)
             cpu = {"value": best, "unit": "instances/s", "cores": cores, "kind": kind,
                    "sample": f"{meta['cpu_sample']} instances of {args.workload}, best of 3 passes "
                              f"({sum(times):.1f} s of CPU work), OpenMP static loop over the ppx call chain"}

@@ -1,0 +1,111 @@
+"""bench_cpu.py -- the CPU legs of bench.py (cpu_baseline and --impl reference).
+
+This is the one place outside tests/ and __graft_entry__.smoke() that executes anything under oracle/: it times
+the reference's own CPU routines (oracle/_ref/libppx_ref.so, the ppx headers behind ref_shim.cpp) or, when that
+was not built, the C restatement, as the BASELINE the GPU numbers are reported next to.  It is never on the
+product path: matrix_b200 does not import it.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from matrix_b200 import synth  # noqa: E402
+
+
+def load_cpu_oracle():
+    """-> (Oracle, kind): the compiled reference if oracle/_ref is there, else the C restatement."""
+    from oracle_lib import Oracle, available
+    if available("ref"):
+        return Oracle("ref"), "reference"
+    so = os.path.join(ROOT, "oracle", "libppx_oracle_fma.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "port"], stdout=subprocess.DEVNULL)
+    return Oracle("port_fma"), "port"
+
+
+_dp = C.POINTER(C.c_double)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _ok(rc):
+    if rc != 0:
+        raise RuntimeError(f"CPU oracle call failed (rc={rc})")
+
+
+def _touch(*arrays):
+    for a in arrays:
+        a.fill(0)  # fault the pages in before timing
+
+
+def cpu_ur5_fk_jacobian(oracle, n, first=0):
+    S = np.ascontiguousarray(synth.UR5_SCREWS)
+    M = np.ascontiguousarray(synth.UR5_HOME)
+    q = synth.joint_angles(n, first=first)
+    T, Js = np.empty((n, 16)), np.empty((n, 36))
+    _touch(T, Js)
+    return lambda: _ok(oracle.lib.ppxo_poe_fk_jacobian(_d(S), _d(M), C.c_int(6), _d(q), _d(T), _d(Js), C.c_size_t(n),
+                                                       C.c_int(0)))
+
+
+def cpu_se3_exp_log(oracle, n, first=0):
+    xi = synth.se3_twists(n, first=first)
+    out = np.empty_like(xi)
+    _touch(out)
+    return lambda: _ok(oracle.lib.ppxo_se3_exp_log(_d(xi), _d(out), C.c_size_t(n), C.c_int(0)))
+
+
+def cpu_linsolve_qr_4x3(oracle, n, first=0):
+    A, b = synth.lstsq_4x3(n, first=first)
+    x = np.empty((n, 3))
+    st = np.empty(n, dtype=np.int8)
+    _touch(x, st)
+    return lambda: _ok(oracle.lib.ppxo_linsolve_qr(C.c_int(4), C.c_int(3), _d(A), _d(b), _d(x),
+                                                   st.ctypes.data_as(C.POINTER(C.c_byte)), C.c_size_t(n), C.c_int(0)))
+
+
+def cpu_svd_6x6(oracle, n, first=0):
+    A = synth.dense(n, 6, 6, first=first)
+    U, w, V = np.empty((n, 36)), np.empty((n, 6)), np.empty((n, 36))
+    _touch(U, w, V)
+    return lambda: _ok(oracle.lib.ppxo_svd(C.c_int(6), C.c_int(6), _d(A), _d(U), _d(w), _d(V), C.c_size_t(n),
+                                           C.c_int(0)))
+
+
+def cpu_eig_sym_4(oracle, n, first=0):
+    S = synth.symmetric(n, 4, first=first)
+    d, z = np.empty((n, 4)), np.empty((n, 16))
+    _touch(d, z)
+    return lambda: _ok(oracle.lib.ppxo_eig_sym(C.c_int(4), _d(S), _d(d), _d(z), C.c_int(1), C.c_size_t(n),
+                                               C.c_int(0)))
+
+
+def cpu_ik_newton_step(oracle, n, first=0):
+    S = np.ascontiguousarray(synth.UR5_SCREWS)
+    M = np.ascontiguousarray(synth.UR5_HOME)
+    q = synth.joint_angles(n, first=first, seed=synth.SEEDS["ik_newton_step"])
+    Tt = oracle.poe_fk_jacobian(S, M, q + synth.ik_offsets(n, first=first), want_Js=False)[0]
+    qo, Vs = np.empty((n, 6)), np.empty((n, 6))
+    _touch(qo, Vs)
+    return lambda: _ok(oracle.lib.ppxo_ik_newton_step(_d(S), _d(M), C.c_int(6), _d(q), _d(Tt), _d(qo), _d(Vs),
+                                                      C.c_size_t(n), C.c_int(0)))
+
+
+
+CPU = {
+    "ur5_fk_jacobian": cpu_ur5_fk_jacobian,
+    "se3_exp_log": cpu_se3_exp_log,
+    "linsolve_qr_4x3": cpu_linsolve_qr_4x3,
+    "svd_6x6": cpu_svd_6x6,
+    "eig_sym_4": cpu_eig_sym_4,
+    "ik_newton_step": cpu_ik_newton_step,
+}

@@ -1,0 +1,147 @@
+// host_api_test.cpp -- the reference's own test bodies for the hot path (test/lie_test.cpp, test/matrix_test.cpp),
+// replayed against include/ppx/ppx.hpp: same names, same literals, same EPS_SP comparison (Matrix::operator==).
+// Every numerical routine below runs on the GPU through libppx_cuda.so.  Built and run by
+// tests/test_gpu_parity.py::test_cpp_host_api (C++14, g++).
+#include <cstdio>
+#include <vector>
+
+#include "ppx/ppx.hpp"
+
+using namespace ppx;
+
+static int failures = 0;
+#define EXPECT(cond)                                                      \
+    do                                                                    \
+    {                                                                     \
+        if (!(cond))                                                      \
+        {                                                                 \
+            std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            ++failures;                                                   \
+        }                                                                 \
+    } while (0)
+
+constexpr double DEG_RAD(double deg) { return deg * PI / 180.0; }
+
+template <std::size_t M, std::size_t N>
+double norm2(const Matrix<M, N> &v)
+{
+    double s = 0;
+    for (double x : v)
+        s += x * x;
+    return std::sqrt(s);
+}
+
+int main()
+{
+    // test/lie_test.cpp:136-142
+    {
+        Matrix<3, 1> vec{1, 2, 3};
+        SO3 expected{0, 3, -2, -3, 0, 1, 2, -1, 0};
+        SO3 result = hat(vec);
+        EXPECT(result == expected);
+    }
+    // test/lie_test.cpp:144-154
+    for (int i = -179; i < 180; i += 7)
+    {
+        so3 w{0.0, 0.0, DEG_RAD((double)i)};
+        auto R = w.exp();
+        EXPECT(SO3::RotZ(DEG_RAD((double)i)) == R);
+        auto dR = R.log();
+        EXPECT(norm2(dR - w) < EPS_SP);
+    }
+    // test/lie_test.cpp:156-168
+    {
+        SE3 Tinput{1, 0, 0, 0, 0, 0, 1, 0, 0, -1, 0, 0, 0, 0, 3, 1};
+        Matrix<4, 4> expected{0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.57079633, 0.0, 0.0, -1.57079633, 0.0, 0.0, 0.0, 2.35619449, 2.35619449, 0.0};
+        auto result = hat(Tinput.log());
+        EXPECT(result == expected);
+    }
+    // test/lie_test.cpp:170-182
+    {
+        Matrix<4, 4> se3mat = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, PI / 2.0, 0.0, 0.0, -PI / 2.0, 0.0, 0.0, 0.0, 2.3562, 2.3562, 0.0};
+        SE3 result{SO3{1, 0, 0, 0, 0, 1, 0, -1, 0}, T3{0, 0, 3}};
+        auto cal = vee(se3mat).exp();
+        for (std::size_t i = 0; i < 16; i++)
+            EXPECT(std::fabs(cal[i] - result[i]) < 1.0e-5);
+    }
+    // test/lie_test.cpp:184-216
+    kinematics<6> UR5;
+    SE3 F6{-1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.817, 0.191, -0.006, 1.0};
+    UR5.setJoint<0>({"R1", se3{0, 0, 1, 0, 0, 0, 0}, SE3()});
+    UR5.setJoint<1>({"R2", se3{0.0, 1.0, 0.0, -0.089, 0.0, 0.0}, SE3{}});
+    UR5.setJoint<2>({"R3", se3{0.0, 1.0, 0.0, -0.089, 0.0, 0.425}, SE3{}});
+    UR5.setJoint<3>({"R4", se3{0.0, 1.0, 0.0, -0.089, 0.0, 0.817}, SE3{}});
+    UR5.setJoint<4>({"R5", se3{0.0, 0.0, -1.0, -0.109, 0.817, 0.0}, SE3{}});
+    UR5.setJoint<5>({"R6", se3{0.0, 1.0, 0.0, 0.006, 0.0, 0.817}, F6});
+    {
+        SE3 result{0.0, 1.0, 0.0, 0.0, -1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.095, 0.109, 0.988, 1.0};
+        kinematics<6>::Q q{0.0, -0.5 * PI, 0.0, 0.0, 0.5 * PI, 0.0};
+        auto r = UR5.forwardSpace(q);
+        EXPECT(r == result);
+        // column 0 = S_0 as in demo/robotics.hpp:97 (the test's private copy leaves it zero)
+        Matrix<6, 6> result2{0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, -0.089, 0.0, 0.0, 0.0, 1.0, 0.0, -0.514, 0.0, 0.0,
+                             0.0, 1.0, 0.0, -0.906, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.906, -0.109, 0.0, 0.0, 1.0, 0.109, -0.095, 0.0};
+        auto r2 = UR5.jacobiSpace(q);
+        EXPECT(r2 == result2);
+        SE3 TargetPose{0.0, 1.0, 0.0, 0.0, -1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.095, 0.109, 0.988, 1.0};
+        auto j = UR5.inverseSpace(TargetPose, {0.0, -1.5, 0.0, 0.0, 1.5, 0.0});
+        EXPECT(UR5.forwardSpace(j) == TargetPose);
+    }
+    // test/matrix_test.cpp:819-850 with the documented spellings of README.md:70-95
+    {
+        Matrix<4, 3> X{3.5, 1.6, 3.7, 4.3, 2.7, -5.7, -0.8, -9.8, -3.1, -6.0, 1.9, 6.9};
+        Matrix<4, 1> Y{1, 1, 1, 1};
+        Matrix<3, 1> result{0.271349846985587, -0.030388140654028, -0.062228084118990};
+        auto x1 = linsolve<Factorization::QR>(X, Y);
+        auto x2 = linsolve<factorization::SVD>(X, Y);
+        EXPECT(x1.x == result);
+        EXPECT(x2.x == result);
+        EXPECT(x1.s == StatusCode::NORMAL);
+        Matrix<4, 3> u{1, 4, 7, 11, 2, 5, 8, 1, 3, 6, 9, 5};
+        SVD<4, 3> ru(u);
+        EXPECT(ru.u * ru.w.diag() * ru.v.T() == u);
+        Matrix<3, 1> w;
+        Matrix<3, 3> v;
+        bool sing = true;
+        auto uu = svdcmp(u, w, v, sing);
+        EXPECT(uu * w.diag() * v.T() == u && !sing);
+        Matrix<4, 4> g{2, -1, 1, 4, -1, 2, -1, 1, 1, -1, 2, -2, 4, 1, -2, 3};
+        EigenValue<4> e1(g, true);
+        Matrix<4, 1> result2{-2.674416988218162, 1.0, 3.945104914279287, 6.729312073938871};
+        EXPECT(e1.d == result2);
+        EXPECT(eig<eigensystem::SymOnlyVal>(g) == result2);
+        auto ev = eig<eigensystem::SymValAndVecSorted>(g);
+        EXPECT(g * ev.vec == ev.vec * ev.val.diag()); // eigenvectors are defined up to sign: check S z = z d
+    }
+    // the batched entry points on host vectors of reference records
+    {
+        const std::size_t n = 100000;
+        std::vector<kinematics<6>::Q> q(n);
+        for (std::size_t i = 0; i < n; i++)
+            for (int k = 0; k < 6; k++)
+                q[i][k] = std::sin(0.001 * (double)(i * 6 + k)) * PI;
+        std::vector<SE3> T(n);
+        std::vector<Matrix<6, 6>> Js(n);
+        cuda::batch_fk_jacobian(UR5, q.data(), T.data(), Js.data(), n);
+        EXPECT(T[777] == UR5.forwardSpace(q[777]));
+        EXPECT(Js[99999] == UR5.jacobiSpace(q[99999]));
+        std::vector<se3> xi(n), back(n);
+        for (std::size_t i = 0; i < n; i++)
+            xi[i] = se3{0.3 * std::sin(i), 0.2, -0.4 * std::cos(i), 1.0, -2.0, 0.5};
+        cuda::batch_exp_log(xi.data(), back.data(), n);
+        EXPECT(back[4242] == xi[4242]);
+        std::vector<Matrix<4, 3>> A(n);
+        std::vector<Matrix<4, 1>> b(n);
+        for (std::size_t i = 0; i < n; i++)
+        {
+            for (int k = 0; k < 12; k++)
+                A[i][k] = std::cos(1.7 * (double)(i * 12 + k));
+            b[i] = {1, 1, 1, 1};
+        }
+        std::vector<EqnResult<3>> res(n);
+        cuda::batch_linsolve<factorization::QR>(A.data(), b.data(), res.data(), n);
+        EXPECT(res[31337].x == linsolve<factorization::SVD>(A[31337], b[31337]).x);
+    }
+    std::printf(failures ? "host_api_test: %d FAILURES\n" : "host_api_test: all passed\n", failures);
+    return failures ? 1 : 0;
+}

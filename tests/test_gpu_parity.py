@@ -537,3 +537,18 @@ def test_full_size_round_trip_1M(mb):
     back = mb.se3_exp_log(xi)
     err = (back - xi).abs().max(dim=1).values / xi.abs().max(dim=1).values
     assert err.max().item() < 1e-11
+
+
+# --------------------------------------------------------------------------------------- C++ host API
+def test_cpp_host_api(mb, tmp_path):
+    """include/ppx/ppx.hpp (C++14): the reference's own test bodies, replayed on the GPU (tests/cpp/host_api_test.cpp)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "host_api_test"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O1", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "host_api_test.cpp"), "-L",
+                           os.path.join(root, "matrix_b200"), "-lppx_cuda",
+                           f"-Wl,-rpath,{os.path.join(root, 'matrix_b200')}", "-o", str(exe)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "all passed" in r.stdout, r.stdout + r.stderr
