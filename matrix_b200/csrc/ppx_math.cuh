@@ -513,84 +513,223 @@ PPX_DEV int linsolve_qr(double (&A)[M * N], double (&b)[M], double (&x)[N])
 }
 
 // ------------------------------------------------------------------------------------------------
-// Jacobi rotation that annihilates the off-diagonal g of [[a, g], [g, b]]:
-// t = tan, with t = 2g / (d + sign(d) sqrt(d^2 + 4 g^2)), d = b - a;  c = 1/sqrt(1+t^2), s = t c.
-PPX_DEV void jacobi_cs(double a, double b, double g, double &c, double &s, double &t)
+// Branch-free reciprocal square root / reciprocal: the hardware seed (MUFU.RSQ64H / MUFU.RCP64H, relative
+// error ~2^-22) refined by one third-order step, full fp64 accuracy for normal, non-zero arguments.  Unlike
+// sqrt() and operator/ there is no special-case slow path, hence no call and no convergence barrier in the
+// instruction stream: the independent rotation chains of a Jacobi round stay in one basic block and overlap.
+// (x = 0 gives inf/NaN; callers discard that lane's result with a select.)
+PPX_DEV double rsqrt_nr(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0); // 1 - x y^2
+    return fma(y * e, fma(0.375, e, 0.5), y); // y (1 + e/2 + 3 e^2/8)
+}
+PPX_DEV double rcp_nr(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0); // 1 - x y
+    return fma(y, fma(e, e, e), y);   // y (1 + e + e^2)
+}
+
+// Jacobi rotation that annihilates the off-diagonal g of [[a, g], [g, b]]: with d = b - a, h = sqrt(d^2 + 4 g^2),
+// u = |d| + h the tangent is t = sign(d) 2g / u, and  c = u / sqrt(u^2 + 4 g^2),  s = sign(d) 2g / sqrt(u^2 + 4 g^2)
+// -- two reciprocal square roots, no division.
+PPX_DEV void jacobi_cs(double a, double b, double g, double &c, double &s)
 {
     const double d = b - a;
-    const double h = sqrt(fma(d, d, 4.0 * g * g));
-    const double den = d >= 0.0 ? d + h : d - h;
-    t = (g != 0.0) ? 2.0 * g / den : 0.0;
-    c = rsqrt(fma(t, t, 1.0));
-    s = t * c;
+    const double g2 = g + g;
+    const double gg = g2 * g2;
+    const double r = fma(d, d, gg);
+    const double h = r * rsqrt_nr(r);
+    const double u = fabs(d) + h;
+    const double w = rsqrt_nr(fma(u, u, gg));
+    c = u * w;
+    s = (d >= 0.0 ? g2 : -g2) * w;
+}
+// ... and the tangent as well (the two-sided update of the diagonal needs it)
+PPX_DEV void jacobi_cst(double a, double b, double g, double &c, double &s, double &t)
+{
+    const double d = b - a;
+    const double g2 = g + g;
+    const double gg = g2 * g2;
+    const double r = fma(d, d, gg);
+    const double h = r * rsqrt_nr(r);
+    const double u = fabs(d) + h;
+    const double w = rsqrt_nr(fma(u, u, gg));
+    const double sg = d >= 0.0 ? g2 : -g2;
+    c = u * w;
+    s = sg * w;
+    t = sg * rcp_nr(u);
+}
+
+// Round-robin ("tournament") ordering of the N(N-1)/2 index pairs: ROUNDS rounds of SLOTS mutually
+// disjoint pairs (circle method; odd N plays against a dummy index N that is skipped).  Disjoint pairs touch
+// different columns, so the long dependent chains that produce each rotation (dot products, square root,
+// division, reciprocal square root) are independent within a round and the compiler interleaves them --
+// that instruction-level parallelism is what keeps the fp64 pipe busy at 2 warps per scheduler.
+template <int N>
+struct Tournament
+{
+    static constexpr int E = N + (N & 1); // even number of players
+    static constexpr int ROUNDS = E - 1;
+    static constexpr int SLOTS = E / 2;
+    __host__ __device__ static constexpr int first(int r, int k) { return k == 0 ? E - 1 : (r + k) % (E - 1); }
+    __host__ __device__ static constexpr int second(int r, int k) { return k == 0 ? r : (r - k + (E - 1)) % (E - 1); }
+    __host__ __device__ static constexpr int lo(int r, int k) { return first(r, k) < second(r, k) ? first(r, k) : second(r, k); }
+    __host__ __device__ static constexpr int hi(int r, int k) { return first(r, k) < second(r, k) ? second(r, k) : first(r, k); }
+    __host__ __device__ static constexpr bool valid(int r, int k) { return hi(r, k) < N; }
+};
+
+// One rotation of the one-sided Jacobi SVD on the columns at positions p and p+1, derived in two phases so that
+// the rotations of a round (disjoint positions) can be derived together: their chains are independent and overlap.
+template <int M>
+PPX_DEV void svd_pair_derive(const double (&ap)[M], const double (&aq)[M], double &np_, double &nq_, double tol2,
+                             double &c, double &s, bool &act)
+{
+    double ga = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; i++)
+        ga = fma(ap[i], aq[i], ga);
+    act = ga * ga > tol2 * (np_ * nq_);
+    double t;
+    jacobi_cst(np_, nq_, ga, c, s, t);
+    c = act ? c : 1.0;
+    s = act ? s : 0.0;
+    t = act ? t : 0.0;
+    // the rotated columns SWAP positions (odd-even transposition ordering): so do their norms
+    const double n0 = fma(-t, ga, np_), n1 = fma(t, ga, nq_);
+    np_ = n1;
+    nq_ = n0;
+}
+
+// x' = c x - s y,  y' = s x + c y, stored swapped: position p gets y', position p+1 gets x'
+template <int L>
+PPX_DEV void rotate_swap(double (&xp)[L], double (&xq)[L], double c, double s)
+{
+#pragma unroll
+    for (int i = 0; i < L; i++)
+    {
+        const double x = xp[i], y = xq[i];
+        xp[i] = fma(s, x, c * y);
+        xq[i] = fma(c, x, -s * y);
+    }
+}
+
+template <int L>
+PPX_DEV void swap_cols(double (&xp)[L], double (&xq)[L])
+{
+#pragma unroll
+    for (int i = 0; i < L; i++)
+    {
+        const double x = xp[i];
+        xp[i] = xq[i];
+        xq[i] = x;
+    }
+}
+
+// One round of the odd-even ordering: positions (START, START+1), (START+2, START+3), ...
+template <int M, int N, int START, bool WANT_V>
+PPX_DEV void svd_round(double (&a)[N][M], double (&v)[N][N], double (&nrm)[N], double tol2, bool &rotated)
+{
+    constexpr int P = (N - START) / 2;
+    double c[P > 0 ? P : 1], s[P > 0 ? P : 1];
+    bool act[P > 0 ? P : 1];
+#pragma unroll
+    for (int k = 0; k < P; k++)
+    {
+        svd_pair_derive<M>(a[START + 2 * k], a[START + 2 * k + 1], nrm[START + 2 * k], nrm[START + 2 * k + 1], tol2,
+                           c[k], s[k], act[k]);
+        rotated |= act[k];
+    }
+#pragma unroll
+    for (int k = 0; k < P; k++)
+    {
+        // always applied, also when no lane needs it (c = 1, s = 0 is then the plain swap): a warp-uniform skip
+        // would save the multiply-adds of the last sweep but costs register moves at every merge point of the
+        // rolled loop -- measured slower
+        rotate_swap<M>(a[START + 2 * k], a[START + 2 * k + 1], c[k], s[k]);
+        if (WANT_V)
+            rotate_swap<N>(v[START + 2 * k], v[START + 2 * k + 1], c[k], s[k]);
+    }
 }
 
 // One-sided (Hestenes) Jacobi SVD of an M x N matrix held column-major in registers:
 // on return A holds U diag(w) (columns = w_j u_j), w2[j] = |column j|^2, V the accumulated rotations.
-// Sweeps stop when a whole sweep (for every lane of the warp) made no rotation above the
-// fp64 threshold, so a warp never diverges inside the loop.
+//
+// Odd-even transposition ordering (Luk & Park): even rounds rotate the neighbouring positions (0,1), (2,3), ...,
+// odd rounds (1,2), (3,4), ..., and every rotation leaves its two columns SWAPPED.  After N rounds every pair of
+// columns has met exactly once and the column order is reversed.  The swap is free -- the rotation just writes its
+// two results to the opposite registers -- so, unlike a round-robin schedule, every round runs the same code on
+// the same registers with no data movement at all, and the sweep is a rolled loop over (even round, odd round):
+// ~8 KB of SASS instead of ~25 KB for an unrolled sweep, which is what the instruction cache needs at 2 warps
+// per scheduler (ncu on the unrolled form: more warp-cycles stalled on `no_instruction` than issuing).
+//
+// A pair is rotated while |a_p . a_q| > tol |a_p| |a_q| with tol = 4 sqrt(M) eps (LAPACK's dgesvj uses
+// sqrt(M) eps; the singular values come out with relative accuracy ~ tol).  Sweeps stop when a whole sweep
+// rotated nothing in any lane of the warp.  Squared column norms are recomputed at the start of every sweep and
+// carried through its rotations (a rotation by tangent t moves t*gamma from one norm to the other).
 template <int M, int N, bool WANT_V>
 PPX_DEV void jacobi_svd_core(double (&A)[M * N], double (&V)[N * N], double (&w2)[N])
 {
-    if (WANT_V)
-    {
-#pragma unroll
-        for (int i = 0; i < N * N; i++)
-            V[i] = (i % (N + 1) == 0) ? 1.0 : 0.0;
-    }
-    constexpr int MAX_SWEEPS = 12;
-    for (int sweep = 0; sweep < MAX_SWEEPS; sweep++)
-    {
-        bool rotated = false;
-#pragma unroll
-        for (int p = 0; p < N - 1; p++)
-#pragma unroll
-            for (int q = p + 1; q < N; q++)
-            {
-                double al = 0.0, be = 0.0, ga = 0.0;
-#pragma unroll
-                for (int i = 0; i < M; i++)
-                {
-                    al = fma(A[i + p * M], A[i + p * M], al);
-                    be = fma(A[i + q * M], A[i + q * M], be);
-                    ga = fma(A[i + p * M], A[i + q * M], ga);
-                }
-                // converged pair: |a_p . a_q| <= eps |a_p| |a_q|
-                const bool act = ga * ga > (EPS_DP * EPS_DP) * al * be;
-                rotated |= act;
-                double c, s, t;
-                jacobi_cs(al, be, ga, c, s, t);
-                c = act ? c : 1.0;
-                s = act ? s : 0.0;
-#pragma unroll
-                for (int i = 0; i < M; i++)
-                {
-                    const double x = A[i + p * M], y = A[i + q * M];
-                    A[i + p * M] = fma(c, x, -s * y);
-                    A[i + q * M] = fma(s, x, c * y);
-                }
-                if (WANT_V)
-                {
-#pragma unroll
-                    for (int i = 0; i < N; i++)
-                    {
-                        const double x = V[i + p * N], y = V[i + q * N];
-                        V[i + p * N] = fma(c, x, -s * y);
-                        V[i + q * N] = fma(s, x, c * y);
-                    }
-                }
-            }
-        if (!__any_sync(0xffffffffu, rotated))
-            break;
-    }
+    double a[N][M], v[N][N], nrm[N];
 #pragma unroll
     for (int j = 0; j < N; j++)
     {
-        double s = 0.0;
 #pragma unroll
         for (int i = 0; i < M; i++)
-            s = fma(A[i + j * M], A[i + j * M], s);
-        w2[j] = s;
+            a[j][i] = A[i + j * M];
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            v[j][i] = (i == j) ? 1.0 : 0.0;
+    }
+    constexpr double TOL2 = 16.0 * M * EPS_DP * EPS_DP;
+    constexpr int MAX_SWEEPS = 12;
+    bool reversed = false;
+    for (int sweep = 0; sweep < MAX_SWEEPS; sweep++)
+    {
+#pragma unroll
+        for (int j = 0; j < N; j++)
+        {
+            double a2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < M; i++)
+                a2 = fma(a[j][i], a[j][i], a2);
+            nrm[j] = a2;
+        }
+        bool rotated = false;
+#pragma unroll 1
+        for (int it = 0; it < N / 2; it++)
+        {
+            svd_round<M, N, 0, WANT_V>(a, v, nrm, TOL2, rotated);
+            svd_round<M, N, 1, WANT_V>(a, v, nrm, TOL2, rotated);
+        }
+        if (N & 1)
+            svd_round<M, N, 0, WANT_V>(a, v, nrm, TOL2, rotated);
+        reversed = !reversed;
+        if (!__any_sync(0xffffffffu, rotated))
+            break;
+    }
+    // an odd number of sweeps leaves the columns in reverse order: undo it (the sweep count is warp-uniform)
+#pragma unroll
+    for (int j = 0; j < N; j++)
+    {
+        double s2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; i++)
+        {
+            const double x = reversed ? a[N - 1 - j][i] : a[j][i];
+            A[i + j * M] = x;
+            s2 = fma(x, x, s2);
+        }
+        w2[j] = s2;
+        if (WANT_V)
+        {
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                V[i + j * N] = reversed ? v[N - 1 - j][i] : v[j][i];
+        }
     }
 }
 
@@ -650,51 +789,70 @@ PPX_DEV void jacobi_eig_sym(const double (&S)[N * N], bool sorted, double (&d)[N
         for (int i = 0; i < N * N; i++)
             Z[i] = (i % (N + 1) == 0) ? 1.0 : 0.0;
     }
-    // an off-diagonal is negligible once g^2 <= (eps/N)^2 |S|_F^2: the eigenvalues then carry an
-    // absolute error of a few eps |S|_2, the same guarantee the reference's QL iteration gives
-    const double thr2 = (EPS_DP / N) * (EPS_DP / N) * fro2;
+    // an off-diagonal is negligible once |g| <= eps |S|_F / 2: the eigenvalues then carry an absolute error of
+    // a few eps |S|_2, the same guarantee the reference's QL iteration gives (|e| < eps (|d_m| + |d_m+1|))
+    const double thr2 = 0.25 * EPS_DP * EPS_DP * fro2;
+    using TT = Tournament<N>;
     constexpr int MAX_SWEEPS = 12;
     for (int sweep = 0; sweep < MAX_SWEEPS; sweep++)
     {
         bool rotated = false;
 #pragma unroll
-        for (int p = 0; p < N - 1; p++)
+        for (int r = 0; r < TT::ROUNDS; r++)
+        {
+            // the pairs of a round are disjoint: rotating (p,q) leaves a_p'p', a_q'q', a_p'q' of the other pairs
+            // untouched, so all rotations of the round can be derived first (independent chains) and applied after
+            double c[TT::SLOTS], s[TT::SLOTS], t[TT::SLOTS];
+            bool act[TT::SLOTS];
 #pragma unroll
-            for (int q = p + 1; q < N; q++)
+            for (int k = 0; k < TT::SLOTS; k++)
             {
+                if (!TT::valid(r, k))
+                    continue;
+                const int p = TT::lo(r, k), q = TT::hi(r, k);
                 const double g = a[sym_ix(p, q, N)];
-                const double app = a[sym_ix(p, p, N)], aqq = a[sym_ix(q, q, N)];
-                const bool act = g * g > thr2;
-                rotated |= act;
-                double c, s, t;
-                jacobi_cs(app, aqq, g, c, s, t);
-                c = act ? c : 1.0;
-                s = act ? s : 0.0;
-                t = act ? t : 0.0;
-                a[sym_ix(p, p, N)] = fma(-t, g, app);
-                a[sym_ix(q, q, N)] = fma(t, g, aqq);
-                a[sym_ix(p, q, N)] = act ? 0.0 : g;
+                act[k] = g * g > thr2;
+                jacobi_cst(a[sym_ix(p, p, N)], a[sym_ix(q, q, N)], g, c[k], s[k], t[k]);
+                c[k] = act[k] ? c[k] : 1.0;
+                s[k] = act[k] ? s[k] : 0.0;
+                t[k] = act[k] ? t[k] : 0.0;
+                rotated |= act[k];
+            }
 #pragma unroll
-                for (int r = 0; r < N; r++)
+            for (int k = 0; k < TT::SLOTS; k++)
+            {
+                if (!TT::valid(r, k))
+                    continue;
+                const int p = TT::lo(r, k), q = TT::hi(r, k);
+                if (__any_sync(0xffffffffu, act[k]))
                 {
-                    if (r != p && r != q)
+                    const double g = a[sym_ix(p, q, N)];
+                    a[sym_ix(p, p, N)] = fma(-t[k], g, a[sym_ix(p, p, N)]);
+                    a[sym_ix(q, q, N)] = fma(t[k], g, a[sym_ix(q, q, N)]);
+                    a[sym_ix(p, q, N)] = act[k] ? 0.0 : g;
+#pragma unroll
+                    for (int i = 0; i < N; i++)
                     {
-                        const double x = a[sym_ix(r, p, N)], y = a[sym_ix(r, q, N)];
-                        a[sym_ix(r, p, N)] = fma(c, x, -s * y);
-                        a[sym_ix(r, q, N)] = fma(s, x, c * y);
+                        if (i != p && i != q)
+                        {
+                            const double x = a[sym_ix(i, p, N)], y = a[sym_ix(i, q, N)];
+                            a[sym_ix(i, p, N)] = fma(c[k], x, -s[k] * y);
+                            a[sym_ix(i, q, N)] = fma(s[k], x, c[k] * y);
+                        }
                     }
-                }
-                if (WANT_Z)
-                {
-#pragma unroll
-                    for (int r = 0; r < N; r++)
+                    if (WANT_Z)
                     {
-                        const double x = Z[r + p * N], y = Z[r + q * N];
-                        Z[r + p * N] = fma(c, x, -s * y);
-                        Z[r + q * N] = fma(s, x, c * y);
+#pragma unroll
+                        for (int i = 0; i < N; i++)
+                        {
+                            const double x = Z[i + p * N], y = Z[i + q * N];
+                            Z[i + p * N] = fma(c[k], x, -s[k] * y);
+                            Z[i + q * N] = fma(s[k], x, c[k] * y);
+                        }
                     }
                 }
             }
+        }
         if (!__any_sync(0xffffffffu, rotated))
             break;
     }

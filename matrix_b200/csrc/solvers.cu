@@ -42,7 +42,7 @@ struct OpLinsolveQR
 template <int M, int N, bool WANT_U, bool WANT_V>
 struct OpSVD
 {
-    static constexpr int BLOCK = 128, MINB = 1, MAXW = (M * N > N * N ? M * N : N * N);
+    static constexpr int BLOCK = 128, MINB = (M * N >= 36 ? 2 : 4), MAXW = (M * N > N * N ? M * N : N * N);
     const double *A;
     double *U;
     double *w;

@@ -135,7 +135,10 @@ int main()
         for (std::size_t i = 0; i < n; i++)
         {
             for (int k = 0; k < 12; k++)
-                A[i][k] = std::cos(1.7 * (double)(i * 12 + k));
+            {
+                const double h = std::sin(12.9898 * (double)i + 78.233 * (double)k) * 43758.5453; // hash -> (-1, 1)
+                A[i][k] = 2.0 * (h - std::floor(h)) - 1.0;
+            }
             b[i] = {1, 1, 1, 1};
         }
         std::vector<EqnResult<3>> res(n);
