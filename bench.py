@@ -117,7 +117,8 @@ def time_cpu(cpu_factory, sample, passes, warm=1):
         t0 = time.perf_counter()
         fn()
         times.append(time.perf_counter() - t0)
-    return sample / min(times), sample / statistics.mean(times), times, kind, oracle.max_threads()
+    from bench_cpu import NTHREADS
+    return sample / min(times), sample / statistics.mean(times), times, kind, NTHREADS
 
 
 def run_reference_arm(args, rank):
@@ -125,7 +126,7 @@ def run_reference_arm(args, rank):
     from matrix_b200.workloads_meta import META
     if rank != 0:
         return
-    from bench_cpu import CPU, load_cpu_oracle
+    from bench_cpu import CPU, NTHREADS, load_cpu_oracle
     meta = META[args.workload]
     sample = args.n if args.n else meta["cpu_sample"]
     oracle, kind = load_cpu_oracle()
@@ -144,7 +145,7 @@ def run_reference_arm(args, rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "instances_per_step": sample, "layout": "aos (host)",
                    "device": "cpu"},
-        "cpu_baseline": {"value": value, "unit": "instances/s", "cores": oracle.max_threads(), "kind": kind,
+        "cpu_baseline": {"value": value, "unit": "instances/s", "cores": NTHREADS, "kind": kind,
                          "sample": desc},
         "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -18,6 +18,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from matrix_b200 import synth  # noqa: E402
 
+# all the host threads this process may use -- stated explicitly on every call, because launchers such as torchrun
+# export OMP_NUM_THREADS=1 and would silently turn the CPU baseline into a single-thread run
+NTHREADS = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
 
 def load_cpu_oracle():
     """-> (Oracle, kind): the compiled reference if oracle/_ref is there, else the C restatement."""
@@ -54,14 +58,14 @@ def cpu_ur5_fk_jacobian(oracle, n, first=0):
     T, Js = np.empty((n, 16)), np.empty((n, 36))
     _touch(T, Js)
     return lambda: _ok(oracle.lib.ppxo_poe_fk_jacobian(_d(S), _d(M), C.c_int(6), _d(q), _d(T), _d(Js), C.c_size_t(n),
-                                                       C.c_int(0)))
+                                                       C.c_int(NTHREADS)))
 
 
 def cpu_se3_exp_log(oracle, n, first=0):
     xi = synth.se3_twists(n, first=first)
     out = np.empty_like(xi)
     _touch(out)
-    return lambda: _ok(oracle.lib.ppxo_se3_exp_log(_d(xi), _d(out), C.c_size_t(n), C.c_int(0)))
+    return lambda: _ok(oracle.lib.ppxo_se3_exp_log(_d(xi), _d(out), C.c_size_t(n), C.c_int(NTHREADS)))
 
 
 def cpu_linsolve_qr_4x3(oracle, n, first=0):
@@ -70,7 +74,7 @@ def cpu_linsolve_qr_4x3(oracle, n, first=0):
     st = np.empty(n, dtype=np.int8)
     _touch(x, st)
     return lambda: _ok(oracle.lib.ppxo_linsolve_qr(C.c_int(4), C.c_int(3), _d(A), _d(b), _d(x),
-                                                   st.ctypes.data_as(C.POINTER(C.c_byte)), C.c_size_t(n), C.c_int(0)))
+                                                   st.ctypes.data_as(C.POINTER(C.c_byte)), C.c_size_t(n), C.c_int(NTHREADS)))
 
 
 def cpu_svd_6x6(oracle, n, first=0):
@@ -78,7 +82,7 @@ def cpu_svd_6x6(oracle, n, first=0):
     U, w, V = np.empty((n, 36)), np.empty((n, 6)), np.empty((n, 36))
     _touch(U, w, V)
     return lambda: _ok(oracle.lib.ppxo_svd(C.c_int(6), C.c_int(6), _d(A), _d(U), _d(w), _d(V), C.c_size_t(n),
-                                           C.c_int(0)))
+                                           C.c_int(NTHREADS)))
 
 
 def cpu_eig_sym_4(oracle, n, first=0):
@@ -86,7 +90,7 @@ def cpu_eig_sym_4(oracle, n, first=0):
     d, z = np.empty((n, 4)), np.empty((n, 16))
     _touch(d, z)
     return lambda: _ok(oracle.lib.ppxo_eig_sym(C.c_int(4), _d(S), _d(d), _d(z), C.c_int(1), C.c_size_t(n),
-                                               C.c_int(0)))
+                                               C.c_int(NTHREADS)))
 
 
 def cpu_ik_newton_step(oracle, n, first=0):
@@ -97,7 +101,7 @@ def cpu_ik_newton_step(oracle, n, first=0):
     qo, Vs = np.empty((n, 6)), np.empty((n, 6))
     _touch(qo, Vs)
     return lambda: _ok(oracle.lib.ppxo_ik_newton_step(_d(S), _d(M), C.c_int(6), _d(q), _d(Tt), _d(qo), _d(Vs),
-                                                      C.c_size_t(n), C.c_int(0)))
+                                                      C.c_size_t(n), C.c_int(NTHREADS)))
 
 
 

@@ -165,6 +165,9 @@ public:
                 r(i, j) = (*this)(r0 + i, c0 + j);
         return r;
     }
+    // inverse / determinant through LU on the GPU (include/linalg.hpp:933-965); defined after the class
+    Matrix I() const;
+    double det() const;
     // se3 halves (include/matrixs.hpp:732-742)
     template <std::size_t A = M, std::size_t B = N, typename = typename std::enable_if<A == 6 && B == 1>::type>
     Matrix<3, 1> _1() const { return {m_[0], m_[1], m_[2]}; }
@@ -208,6 +211,23 @@ private:
     }
     std::array<double, M * N> m_;
 };
+
+template <std::size_t M, std::size_t N>
+Matrix<M, N> Matrix<M, N>::I() const
+{
+    static_assert(M == N, "only square matrix has an inverse. For rectangular matrix ,query for pinv.");
+    Matrix r;
+    cuda::check(ppx_cuda_host_inverse((int)M, data(), r.data(), 1));
+    return r;
+}
+template <std::size_t M, std::size_t N>
+double Matrix<M, N>::det() const
+{
+    static_assert(M == N, "only square matrix has a determinant.");
+    double d = 0.0;
+    cuda::check(ppx_cuda_host_det((int)M, data(), &d, 1));
+    return d;
+}
 
 template <std::size_t M, std::size_t N>
 using MatrixS = Matrix<M, N>; // the name the reference's headers use
@@ -461,7 +481,57 @@ auto eig(const Matrix<N, N> &s) -> decltype(details::eig_impl<type, N>::run(s))
     return details::eig_impl<type, N>::run(s);
 }
 
-// linsolve<Factorization::QR|SVD>(A, b) (include/linalg.hpp:1189-1209)
+// MatrixS::I(), det(), pinv(), matrix norm2 (include/linalg.hpp:933-965, 1211-1227, 926-931); the reference spells the
+// first two as members, its README as free functions inverse() / determinant()
+template <std::size_t N>
+Matrix<N, N> inverse(const Matrix<N, N> &a)
+{
+    Matrix<N, N> r;
+    cuda::check(ppx_cuda_host_inverse((int)N, a.data(), r.data(), 1));
+    return r;
+}
+template <std::size_t N>
+double determinant(const Matrix<N, N> &a)
+{
+    double d = 0.0;
+    cuda::check(ppx_cuda_host_det((int)N, a.data(), &d, 1));
+    return d;
+}
+template <std::size_t M, std::size_t N>
+Matrix<N, M> pinv(const Matrix<M, N> &a)
+{
+    Matrix<N, M> r;
+    cuda::check(ppx_cuda_host_pinv((int)M, (int)N, a.data(), r.data(), 1));
+    return r;
+}
+// vector norm2 = sqrt(inner_product) (include/linalg.hpp:217-241): a container-level helper, host code
+template <std::size_t M, std::size_t N>
+typename std::enable_if<(M == 1 || N == 1), double>::type norm2(const Matrix<M, N> &a)
+{
+    double s = 0.0;
+    for (double x : a)
+        s += x * x;
+    return std::sqrt(s);
+}
+template <std::size_t M, std::size_t N>
+typename std::enable_if<(M > 1 && N > 1), double>::type norm2(const Matrix<M, N> &a)
+{
+    double s = 0.0;
+    cuda::check(ppx_cuda_host_norm2((int)M, (int)N, a.data(), &s, 1));
+    return s;
+}
+
+// linsolve<Factorization::LU|QR|SVD>(A, b) (include/linalg.hpp:1176-1209)
+template <Factorization type, std::size_t M, std::size_t N>
+typename std::enable_if<type == Factorization::LU, EqnResult<N>>::type linsolve(const Matrix<M, N> &A, Matrix<M, 1> b)
+{
+    static_assert(M == N, "LU decomposation only supports square matrix.");
+    EqnResult<N> r;
+    int8_t st = 0;
+    cuda::check(ppx_cuda_host_linsolve_lu((int)N, A.data(), b.data(), r.x.data(), &st, 1));
+    r.s = static_cast<StatusCode>(st);
+    return r;
+}
 template <Factorization type, std::size_t M, std::size_t N>
 typename std::enable_if<type == Factorization::QR, EqnResult<N>>::type linsolve(const Matrix<M, N> &A, Matrix<M, 1> b)
 {
@@ -632,6 +702,34 @@ typename std::enable_if<type == Factorization::SVD>::type batch_linsolve(const M
     check(ppx_cuda_host_linsolve_svd((int)M, (int)N, dp(A), dp(b), dp(x), n));
     if (status)
         std::fill(status, status + n, StatusCode::NORMAL);
+}
+template <Factorization type, std::size_t M, std::size_t N>
+typename std::enable_if<type == Factorization::LU>::type batch_linsolve(const Matrix<M, N> *A, const Matrix<M, 1> *b,
+                                                                       Matrix<N, 1> *x, StatusCode *status,
+                                                                       std::size_t n)
+{
+    static_assert(M == N, "LU decomposation only supports square matrix.");
+    check(ppx_cuda_host_linsolve_lu((int)N, dp(A), dp(b), dp(x), reinterpret_cast<int8_t *>(status), n));
+}
+template <std::size_t N>
+void batch_inverse(const Matrix<N, N> *A, Matrix<N, N> *Ai, std::size_t n)
+{
+    check(ppx_cuda_host_inverse((int)N, dp(A), dp(Ai), n));
+}
+template <std::size_t N>
+void batch_determinant(const Matrix<N, N> *A, double *det, std::size_t n)
+{
+    check(ppx_cuda_host_det((int)N, dp(A), det, n));
+}
+template <std::size_t M, std::size_t N>
+void batch_pinv(const Matrix<M, N> *A, Matrix<N, M> *P, std::size_t n)
+{
+    check(ppx_cuda_host_pinv((int)M, (int)N, dp(A), dp(P), n));
+}
+template <std::size_t M, std::size_t N>
+void batch_norm2(const Matrix<M, N> *A, double *s, std::size_t n)
+{
+    check(ppx_cuda_host_norm2((int)M, (int)N, dp(A), s, n));
 }
 // ... and into the reference's EqnResult<N> records
 template <Factorization type, std::size_t M, std::size_t N>

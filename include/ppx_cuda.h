@@ -140,6 +140,17 @@ int ppx_cuda_batch_linsolve_svd(int m, int n, const double *A, const double *b, 
 int ppx_cuda_batch_eig_sym(int n, const double *S, double *d, double *z, int sorted, size_t count, int layout,
                            size_t ld, void *stream);
 
+/* linsolve<Factorization::LU>(A, b), :448-533, 1176-1187 (partial pivoting; SINGULAR when a pivot < EPS_DP, x = b) */
+int ppx_cuda_batch_linsolve_lu(int n, const double *A, const double *b, double *x, int8_t *status, size_t count,
+                               int layout, size_t ld, void *stream);
+/* MatrixS::I() and MatrixS::det() through LU, :933-965.  Ai: n*n (all zero when singular); det: 1 double */
+int ppx_cuda_batch_inverse(int n, const double *A, double *Ai, size_t count, int layout, size_t ld, void *stream);
+int ppx_cuda_batch_det(int n, const double *A, double *det, size_t count, int layout, size_t ld, void *stream);
+/* pinv(A), :1211-1227: A m*n -> P n*m, same truncation as SVD::solve */
+int ppx_cuda_batch_pinv(int m, int n, const double *A, double *P, size_t count, int layout, size_t ld, void *stream);
+/* matrix norm2(A) = largest singular value, :926-931: A m*n (m < n allowed) -> 1 double */
+int ppx_cuda_batch_norm2(int m, int n, const double *A, double *s, size_t count, int layout, size_t ld, void *stream);
+
 /* ---- host-buffer face: the same operations on HOST arrays of dense reference records (AoS), i.e. on
  * std::vector<ppx::MatrixS<M,N>>::data().  Each call cuts the batch into chunks that rotate over three
  * streams so the H2D copy, the kernel and the D2H copy of neighbouring chunks overlap; device scratch
@@ -168,6 +179,11 @@ int ppx_cuda_host_linsolve_qr(int m, int n, const double *A, const double *b, do
 int ppx_cuda_host_svd(int m, int n, const double *A, double *U, double *w, double *V, size_t count);
 int ppx_cuda_host_linsolve_svd(int m, int n, const double *A, const double *b, double *x, size_t count);
 int ppx_cuda_host_eig_sym(int n, const double *S, double *d, double *z, int sorted, size_t count);
+int ppx_cuda_host_linsolve_lu(int n, const double *A, const double *b, double *x, int8_t *status, size_t count);
+int ppx_cuda_host_inverse(int n, const double *A, double *Ai, size_t count);
+int ppx_cuda_host_det(int n, const double *A, double *det, size_t count);
+int ppx_cuda_host_pinv(int m, int n, const double *A, double *P, size_t count);
+int ppx_cuda_host_norm2(int m, int n, const double *A, double *s, size_t count);
 
 #ifdef __cplusplus
 }

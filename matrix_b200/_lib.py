@@ -58,6 +58,11 @@ _SIGNATURES = {
     "ppx_cuda_batch_svd": [_i, _i, _vp, _vp, _vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_batch_linsolve_svd": [_i, _i, _vp, _vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_batch_eig_sym": [_i, _vp, _vp, _vp, _i, _sz, _i, _sz, _vp],
+    "ppx_cuda_batch_linsolve_lu": [_i, _vp, _vp, _vp, _vp, _sz, _i, _sz, _vp],
+    "ppx_cuda_batch_inverse": [_i, _vp, _vp, _sz, _i, _sz, _vp],
+    "ppx_cuda_batch_det": [_i, _vp, _vp, _sz, _i, _sz, _vp],
+    "ppx_cuda_batch_pinv": [_i, _i, _vp, _vp, _sz, _i, _sz, _vp],
+    "ppx_cuda_batch_norm2": [_i, _i, _vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_host_so3_exp": [_vp, _vp, _sz],
     "ppx_cuda_host_SO3_log": [_vp, _vp, _sz],
     "ppx_cuda_host_se3_exp": [_vp, _vp, _sz],
@@ -75,6 +80,11 @@ _SIGNATURES = {
     "ppx_cuda_host_svd": [_i, _i, _vp, _vp, _vp, _vp, _sz],
     "ppx_cuda_host_linsolve_svd": [_i, _i, _vp, _vp, _vp, _sz],
     "ppx_cuda_host_eig_sym": [_i, _vp, _vp, _vp, _i, _sz],
+    "ppx_cuda_host_linsolve_lu": [_i, _vp, _vp, _vp, _vp, _sz],
+    "ppx_cuda_host_inverse": [_i, _vp, _vp, _sz],
+    "ppx_cuda_host_det": [_i, _vp, _vp, _sz],
+    "ppx_cuda_host_pinv": [_i, _i, _vp, _vp, _sz],
+    "ppx_cuda_host_norm2": [_i, _i, _vp, _vp, _sz],
 }
 _RESTYPES = {
     "ppx_cuda_version": (C.c_char_p, []),

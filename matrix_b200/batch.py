@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import check, lib
 
 AOS, SOA = 0, 1
-QR, SVD = "QR", "SVD"
+LU, QR, SVD = "LU", "QR", "SVD"
 NORMAL, CONVERGED, DIVERGED, SINGULAR = 0, 1, 2, 3
 
 
@@ -203,7 +203,13 @@ def linsolve(factorization, m, n, A, b, layout=AOS, count=None):
         raise ValueError("A and b must have the same batch shape")
     x, px = _out(A, n, layout, count, ld)
     with torch.cuda.device(A.device):
-        if factorization == QR:
+        if factorization == LU:
+            if m != n:
+                raise ValueError("LU decomposation only supports square matrix.")
+            status = torch.empty(count, dtype=torch.int8, device=A.device)
+            check(lib.ppx_cuda_batch_linsolve_lu(n, pa, pb, px, C.c_void_p(status.data_ptr()), count, layout, ld,
+                                                 _stream()))
+        elif factorization == QR:
             status = torch.empty(count, dtype=torch.int8, device=A.device)
             check(lib.ppx_cuda_batch_linsolve_qr(m, n, pa, pb, px, C.c_void_p(status.data_ptr()), count, layout, ld,
                                                  _stream()))
@@ -212,7 +218,7 @@ def linsolve(factorization, m, n, A, b, layout=AOS, count=None):
             status = torch.zeros(count, dtype=torch.int8, device=A.device)
             check(lib.ppx_cuda_batch_linsolve_svd(m, n, pa, pb, px, count, layout, ld, _stream()))
         else:
-            raise ValueError("factorization must be QR or SVD")
+            raise ValueError("factorization must be LU, QR or SVD")
     return x, status
 
 
@@ -240,6 +246,42 @@ def eig(n, S, sorted=True, vectors=True, layout=AOS, count=None):
     with torch.cuda.device(S.device):
         check(lib.ppx_cuda_batch_eig_sym(n, ps, pd, pz, 1 if sorted else 0, count, layout, ld, _stream()))
     return d, z
+
+
+def inverse(n, A, layout=AOS, count=None):
+    """MatrixS::I(), include/linalg.hpp:933-948 (all-zero result for a singular matrix)"""
+    pa, count, ld = _in(A, n * n, layout, count)
+    Ai, pi = _out(A, n * n, layout, count, ld)
+    with torch.cuda.device(A.device):
+        check(lib.ppx_cuda_batch_inverse(n, pa, pi, count, layout, ld, _stream()))
+    return Ai
+
+
+def det(n, A, layout=AOS, count=None):
+    """MatrixS::det(), include/linalg.hpp:950-965 -> (count, 1) / (1, ld)"""
+    pa, count, ld = _in(A, n * n, layout, count)
+    d, pd = _out(A, 1, layout, count, ld)
+    with torch.cuda.device(A.device):
+        check(lib.ppx_cuda_batch_det(n, pa, pd, count, layout, ld, _stream()))
+    return d
+
+
+def pinv(m, n, A, layout=AOS, count=None):
+    """pinv(A), include/linalg.hpp:1211-1227: (., m*n) -> (., n*m)"""
+    pa, count, ld = _in(A, m * n, layout, count)
+    P, pp = _out(A, m * n, layout, count, ld)
+    with torch.cuda.device(A.device):
+        check(lib.ppx_cuda_batch_pinv(m, n, pa, pp, count, layout, ld, _stream()))
+    return P
+
+
+def norm2(m, n, A, layout=AOS, count=None):
+    """matrix norm2 = largest singular value, include/linalg.hpp:926-931"""
+    pa, count, ld = _in(A, m * n, layout, count)
+    sv, ps = _out(A, 1, layout, count, ld)
+    with torch.cuda.device(A.device):
+        check(lib.ppx_cuda_batch_norm2(m, n, pa, ps, count, layout, ld, _stream()))
+    return sv
 
 
 # ------------------------------------------------------------------------------ utilities

@@ -6,6 +6,7 @@
 // from the stream-ordered allocator and is released before the call returns.  Pinned host memory
 // (ppx_cuda_malloc_host) makes the copies truly asynchronous; pageable memory works but serialises.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "ppx_launch.cuh"
@@ -24,8 +25,27 @@ struct HostOut
     size_t bytes;
 };
 
-constexpr int SLOTS = 3;
-constexpr size_t CHUNK_BYTES = 48u << 20; // per-chunk traffic of the widest side
+constexpr int MAX_SLOTS = 8;
+// defaults: 3 chunks in flight, 48 MiB of traffic on the widest side per chunk; PPX_HOST_SLOTS / PPX_HOST_CHUNK_MIB
+// override them (tuning knobs, read once)
+inline int env_slots()
+{
+    static const int v = [] {
+        const char *e = std::getenv("PPX_HOST_SLOTS");
+        const int n = e ? std::atoi(e) : 3;
+        return n < 1 ? 1 : (n > MAX_SLOTS ? MAX_SLOTS : n);
+    }();
+    return v;
+}
+inline size_t env_chunk_bytes()
+{
+    static const size_t v = [] {
+        const char *e = std::getenv("PPX_HOST_CHUNK_MIB");
+        const long n = e ? std::atol(e) : 48;
+        return (size_t)(n < 1 ? 1 : n) << 20;
+    }();
+    return v;
+}
 
 #define PPX_TRY(expr)                 \
     do                                \
@@ -53,12 +73,13 @@ int pipeline(const std::vector<HostIn> &ins, const std::vector<HostOut> &outs, s
     for (const HostOut &a : outs)
         out_b += a.ptr ? a.bytes : 0;
     const size_t widest = std::max<size_t>(std::max(in_b, out_b), 1);
-    size_t chunk = std::max<size_t>(CHUNK_BYTES / widest, 1024);
+    size_t chunk = std::max<size_t>(env_chunk_bytes() / widest, 1024);
     chunk = (chunk + 1023) / 1024 * 1024;
     chunk = std::min(chunk, n);
 
     int rc = PPX_OK;
-    cudaStream_t st[SLOTS] = {};
+    const int SLOTS = env_slots();
+    cudaStream_t st[MAX_SLOTS] = {};
     std::vector<void *> d_in(SLOTS * ins.size(), nullptr), d_out(SLOTS * outs.size(), nullptr);
     const int nslots = (int)std::min<size_t>(SLOTS, (n + chunk - 1) / chunk);
     for (int s = 0; s < nslots; s++)
@@ -265,6 +286,55 @@ int ppx_cuda_host_eig_sym(int n, const double *S, double *d, double *z, int sort
                         return ppx_cuda_batch_eig_sym(n, (cd)i[0], (md)o[0], (md)o[1], sorted, c, PPX_LAYOUT_AOS, 0,
                                                       s);
                     });
+}
+
+int ppx_cuda_host_linsolve_lu(int n, const double *A, const double *b, double *x, int8_t *status, size_t count)
+{
+    if (n < 1)
+        return PPX_ERR_BAD_SHAPE;
+    return pipeline({{A, (size_t)n * n * D}, {b, (size_t)n * D}}, {{x, (size_t)n * D}, {status, 1}}, count,
+                    [=](size_t c, void **i, void **o, void *s) {
+                        return ppx_cuda_batch_linsolve_lu(n, (cd)i[0], (cd)i[1], (md)o[0], (int8_t *)o[1], c,
+                                                          PPX_LAYOUT_AOS, 0, s);
+                    });
+}
+
+int ppx_cuda_host_inverse(int n, const double *A, double *Ai, size_t count)
+{
+    if (n < 1)
+        return PPX_ERR_BAD_SHAPE;
+    return pipeline({{A, (size_t)n * n * D}}, {{Ai, (size_t)n * n * D}}, count,
+                    [=](size_t c, void **i, void **o, void *s) {
+                        return ppx_cuda_batch_inverse(n, (cd)i[0], (md)o[0], c, PPX_LAYOUT_AOS, 0, s);
+                    });
+}
+
+int ppx_cuda_host_det(int n, const double *A, double *det, size_t count)
+{
+    if (n < 1)
+        return PPX_ERR_BAD_SHAPE;
+    return pipeline({{A, (size_t)n * n * D}}, {{det, D}}, count, [=](size_t c, void **i, void **o, void *s) {
+        return ppx_cuda_batch_det(n, (cd)i[0], (md)o[0], c, PPX_LAYOUT_AOS, 0, s);
+    });
+}
+
+int ppx_cuda_host_pinv(int m, int n, const double *A, double *P, size_t count)
+{
+    if (m < 1 || n < 1)
+        return PPX_ERR_BAD_SHAPE;
+    return pipeline({{A, (size_t)m * n * D}}, {{P, (size_t)m * n * D}}, count,
+                    [=](size_t c, void **i, void **o, void *s) {
+                        return ppx_cuda_batch_pinv(m, n, (cd)i[0], (md)o[0], c, PPX_LAYOUT_AOS, 0, s);
+                    });
+}
+
+int ppx_cuda_host_norm2(int m, int n, const double *A, double *sv, size_t count)
+{
+    if (m < 1 || n < 1)
+        return PPX_ERR_BAD_SHAPE;
+    return pipeline({{A, (size_t)m * n * D}}, {{sv, D}}, count, [=](size_t c, void **i, void **o, void *s) {
+        return ppx_cuda_batch_norm2(m, n, (cd)i[0], (md)o[0], c, PPX_LAYOUT_AOS, 0, s);
+    });
 }
 
 } // extern "C"

@@ -512,6 +512,82 @@ PPX_DEV int linsolve_qr(double (&A)[M * N], double (&b)[M], double (&x)[N])
     return singular ? 3 : 0;
 }
 
+// LU<n> with partial pivoting, include/linalg.hpp:448-533, in registers.  The pivot row is data dependent, so the
+// row exchange is a predicated swap against every candidate row (compile-time indices only).  Pivot choice follows
+// the reference: first row of maximal |A(row,k)|, SINGULAR as soon as that maximum is below EPS_DP (:473-477).
+// The permutation is applied to the right-hand sides as it happens, which is what LU::solve's b[indx[row]] does.
+// NRHS right-hand sides are carried along in B (column-major N x NRHS).  Returns the reference's `even` flag in
+// `even`; on SINGULAR the factorisation stops being meaningful and the caller substitutes the reference's result.
+template <int N, int NRHS>
+PPX_DEV bool lu_factor_solve(double (&A)[N * N], double (&B)[N * (NRHS > 0 ? NRHS : 1)], bool &even)
+{
+    bool singular = false;
+    even = true;
+#pragma unroll
+    for (int k = 0; k < N; k++)
+    {
+        double valmax = fabs(A[k + k * N]);
+        int ip = k;
+#pragma unroll
+        for (int r = k + 1; r < N; r++)
+        {
+            const double t = fabs(A[r + k * N]);
+            const bool better = valmax < t;
+            valmax = better ? t : valmax;
+            ip = better ? r : ip;
+        }
+        singular |= valmax < EPS_DP;
+        even = (ip != k) ? !even : even;
+#pragma unroll
+        for (int r = k + 1; r < N; r++)
+        {
+            const bool sw = (ip == r);
+#pragma unroll
+            for (int c = 0; c < N; c++)
+            {
+                const double x = A[k + c * N], y = A[r + c * N];
+                A[k + c * N] = sw ? y : x;
+                A[r + c * N] = sw ? x : y;
+            }
+#pragma unroll
+            for (int c = 0; c < NRHS; c++)
+            {
+                const double x = B[k + c * N], y = B[r + c * N];
+                B[k + c * N] = sw ? y : x;
+                B[r + c * N] = sw ? x : y;
+            }
+        }
+        const double ipiv = 1.0 / A[k + k * N];
+#pragma unroll
+        for (int r = k + 1; r < N; r++)
+        {
+            const double wgt = A[r + k * N] * ipiv;
+            A[r + k * N] = wgt;
+#pragma unroll
+            for (int c = k + 1; c < N; c++)
+                A[r + c * N] = fma(-wgt, A[k + c * N], A[r + c * N]);
+#pragma unroll
+            for (int c = 0; c < NRHS; c++) // forward substitution fused into the elimination
+                B[r + c * N] = fma(-wgt, B[k + c * N], B[r + c * N]);
+        }
+    }
+    // back substitution, :516-526
+#pragma unroll
+    for (int c = 0; c < NRHS; c++)
+    {
+#pragma unroll
+        for (int r = N - 1; r >= 0; r--)
+        {
+            double sum = B[r + c * N];
+#pragma unroll
+            for (int j = r + 1; j < N; j++)
+                sum = fma(-A[r + j * N], B[j + c * N], sum);
+            B[r + c * N] = sum / A[r + r * N];
+        }
+    }
+    return singular;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Branch-free reciprocal square root / reciprocal: the hardware seed (MUFU.RSQ64H / MUFU.RCP64H, relative
 // error ~2^-22) refined by one third-order step, full fp64 accuracy for normal, non-zero arguments.  Unlike

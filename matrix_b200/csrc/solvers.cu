@@ -113,6 +113,149 @@ struct OpEigSym
     }
 };
 
+// LU<n> / linsolve<Factorization::LU> / MatrixS::I() / det(), include/linalg.hpp:448-533, 933-965,
+// 1176-1187.  HBM-bound like QR.
+template <int N>
+struct OpLinsolveLU
+{
+    static constexpr int BLOCK = 128, MINB = (N <= 4 ? 4 : 2), MAXW = N * N;
+    const double *A;
+    const double *b;
+    double *x;
+    int8_t *status;
+    template <class IO>
+    __device__ __forceinline__ void operator()(const IO &io) const
+    {
+        double a[N * N], rhs[N], b0[N];
+        io.load(A, a);
+        io.load(b, rhs);
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            b0[i] = rhs[i];
+        bool even;
+        const bool singular = lu_factor_solve<N, 1>(a, rhs, even);
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            rhs[i] = singular ? b0[i] : rhs[i]; // linsolve<LU> returns b untouched on SINGULAR (:1182-1186)
+        io.store(x, rhs);
+        if (status != nullptr && io.valid)
+            status[io.i] = singular ? PPX_STATUS_SINGULAR : PPX_STATUS_NORMAL;
+    }
+};
+
+template <int N>
+struct OpInverse
+{
+    static constexpr int BLOCK = 128, MINB = (N <= 4 ? 4 : 2), MAXW = N * N;
+    const double *A;
+    double *Ai;
+    template <class IO>
+    __device__ __forceinline__ void operator()(const IO &io) const
+    {
+        double a[N * N], inv[N * N];
+        io.load(A, a);
+#pragma unroll
+        for (int i = 0; i < N * N; i++)
+            inv[i] = (i % (N + 1) == 0) ? 1.0 : 0.0;
+        bool even;
+        const bool singular = lu_factor_solve<N, N>(a, inv, even);
+#pragma unroll
+        for (int i = 0; i < N * N; i++)
+            inv[i] = singular ? 0.0 : inv[i]; // MatrixS::I() returns {} on SINGULAR (:938-941)
+        io.store(Ai, inv);
+    }
+};
+
+template <int N>
+struct OpDet
+{
+    static constexpr int BLOCK = 128, MINB = (N <= 4 ? 4 : 2), MAXW = N * N;
+    const double *A;
+    double *det;
+    template <class IO>
+    __device__ __forceinline__ void operator()(const IO &io) const
+    {
+        double a[N * N], dummy[N];
+        io.load(A, a);
+        bool even;
+        const bool singular = lu_factor_solve<N, 0>(a, dummy, even);
+        double D = even ? 1.0 : -1.0; // :959-964
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            D *= a[i + i * N];
+        const double out[1] = {singular ? 0.0 : D};
+        io.store(det, out);
+    }
+};
+
+// pinv and the matrix 2-norm are epilogues of the Jacobi SVD (include/linalg.hpp:1211-1227, 926-931)
+template <int M, int N>
+struct OpPinv
+{
+    static constexpr int BLOCK = 128, MINB = (M * N >= 36 ? 1 : 3), MAXW = M * N;
+    const double *A;
+    double *P; // N x M
+    template <class IO>
+    __device__ __forceinline__ void operator()(const IO &io) const
+    {
+        double a[M * N], v[N * N], w2[N], p[N * M];
+        io.load(A, a);
+        jacobi_svd_core<M, N, true>(a, v, w2);
+        double wmax2 = w2[0];
+#pragma unroll
+        for (int j = 1; j < N; j++)
+            wmax2 = fmax(wmax2, w2[j]);
+        const double f = 0.5 * sqrt((double)(M + N + 1)) * EPS_DP;
+        const double tsh2 = f * f * wmax2;
+#pragma unroll
+        for (int i = 0; i < N * M; i++)
+            p[i] = 0.0;
+        // pinv = V diag(1/w) U^T = sum_j v_j a_j^T / w_j^2 over w_j > tsh (a_j = w_j u_j)
+#pragma unroll
+        for (int j = 0; j < N; j++)
+        {
+            const double iw2 = w2[j] > tsh2 ? 1.0 / w2[j] : 0.0;
+#pragma unroll
+            for (int c = 0; c < M; c++)
+            {
+                const double t = a[c + j * M] * iw2;
+#pragma unroll
+                for (int r = 0; r < N; r++)
+                    p[r + c * N] = fma(v[r + j * N], t, p[r + c * N]);
+            }
+        }
+        io.store(P, p);
+    }
+};
+
+// sigma_max; a wide matrix (M < N) is decomposed through its transpose (same singular values)
+template <int M, int N>
+struct OpNorm2
+{
+    static constexpr int R = (M >= N ? M : N), C = (M >= N ? N : M);
+    static constexpr int BLOCK = 128, MINB = (M * N >= 30 ? 2 : 4), MAXW = M * N;
+    const double *A;
+    double *s;
+    template <class IO>
+    __device__ __forceinline__ void operator()(const IO &io) const
+    {
+        double a[M * N], t[R * C], v[C * C], w2[C];
+        io.load(A, a);
+#pragma unroll
+        for (int c = 0; c < C; c++)
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                t[r + c * R] = (M >= N) ? a[r + c * M] : a[c + r * M];
+        jacobi_svd_core<R, C, false>(t, v, w2);
+        double wmax2 = w2[0];
+#pragma unroll
+        for (int j = 1; j < C; j++)
+            wmax2 = fmax(wmax2, w2[j]);
+        const double out[1] = {sqrt(wmax2)};
+        io.store(s, out);
+    }
+};
+
 template <int M, int N>
 int svd_mn(const double *A, double *U, double *w, double *V, size_t count, int layout, size_t ld, void *stream)
 {
@@ -200,6 +343,84 @@ int ppx_cuda_batch_eig_sym(int n, const double *S, double *d, double *z, int sor
     case 5: return eig_n<5>(S, d, z, sorted, count, layout, ld, stream);
     case 6: return eig_n<6>(S, d, z, sorted, count, layout, ld, stream);
     }
+    return PPX_ERR_BAD_SHAPE;
+}
+
+int ppx_cuda_batch_linsolve_lu(int n, const double *A, const double *b, double *x, int8_t *status, size_t count,
+                               int layout, size_t ld, void *stream)
+{
+    if (count == 0)
+        return PPX_OK;
+    PPX_CHECK_PTRS(A, b, x);
+    switch (n)
+    {
+    case 2: return dispatch(layout, OpLinsolveLU<2>{A, b, x, status}, count, ld, stream);
+    case 3: return dispatch(layout, OpLinsolveLU<3>{A, b, x, status}, count, ld, stream);
+    case 4: return dispatch(layout, OpLinsolveLU<4>{A, b, x, status}, count, ld, stream);
+    case 5: return dispatch(layout, OpLinsolveLU<5>{A, b, x, status}, count, ld, stream);
+    case 6: return dispatch(layout, OpLinsolveLU<6>{A, b, x, status}, count, ld, stream);
+    }
+    return PPX_ERR_BAD_SHAPE;
+}
+
+int ppx_cuda_batch_inverse(int n, const double *A, double *Ai, size_t count, int layout, size_t ld, void *stream)
+{
+    if (count == 0)
+        return PPX_OK;
+    PPX_CHECK_PTRS(A, Ai);
+    switch (n)
+    {
+    case 2: return dispatch(layout, OpInverse<2>{A, Ai}, count, ld, stream);
+    case 3: return dispatch(layout, OpInverse<3>{A, Ai}, count, ld, stream);
+    case 4: return dispatch(layout, OpInverse<4>{A, Ai}, count, ld, stream);
+    case 5: return dispatch(layout, OpInverse<5>{A, Ai}, count, ld, stream);
+    case 6: return dispatch(layout, OpInverse<6>{A, Ai}, count, ld, stream);
+    }
+    return PPX_ERR_BAD_SHAPE;
+}
+
+int ppx_cuda_batch_det(int n, const double *A, double *det, size_t count, int layout, size_t ld, void *stream)
+{
+    if (count == 0)
+        return PPX_OK;
+    PPX_CHECK_PTRS(A, det);
+    switch (n)
+    {
+    case 2: return dispatch(layout, OpDet<2>{A, det}, count, ld, stream);
+    case 3: return dispatch(layout, OpDet<3>{A, det}, count, ld, stream);
+    case 4: return dispatch(layout, OpDet<4>{A, det}, count, ld, stream);
+    case 5: return dispatch(layout, OpDet<5>{A, det}, count, ld, stream);
+    case 6: return dispatch(layout, OpDet<6>{A, det}, count, ld, stream);
+    }
+    return PPX_ERR_BAD_SHAPE;
+}
+
+int ppx_cuda_batch_pinv(int m, int n, const double *A, double *P, size_t count, int layout, size_t ld, void *stream)
+{
+    if (count == 0)
+        return PPX_OK;
+    PPX_CHECK_PTRS(A, P);
+    PPX_SHAPE2(6, 6, dispatch(layout, OpPinv<6, 6>{A, P}, count, ld, stream));
+    PPX_SHAPE2(4, 3, dispatch(layout, OpPinv<4, 3>{A, P}, count, ld, stream));
+    PPX_SHAPE2(3, 3, dispatch(layout, OpPinv<3, 3>{A, P}, count, ld, stream));
+    PPX_SHAPE2(4, 4, dispatch(layout, OpPinv<4, 4>{A, P}, count, ld, stream));
+    PPX_SHAPE2(5, 4, dispatch(layout, OpPinv<5, 4>{A, P}, count, ld, stream));
+    PPX_SHAPE2(6, 4, dispatch(layout, OpPinv<6, 4>{A, P}, count, ld, stream));
+    return PPX_ERR_BAD_SHAPE;
+}
+
+int ppx_cuda_batch_norm2(int m, int n, const double *A, double *s, size_t count, int layout, size_t ld, void *stream)
+{
+    if (count == 0)
+        return PPX_OK;
+    PPX_CHECK_PTRS(A, s);
+    PPX_SHAPE2(6, 6, dispatch(layout, OpNorm2<6, 6>{A, s}, count, ld, stream));
+    PPX_SHAPE2(4, 3, dispatch(layout, OpNorm2<4, 3>{A, s}, count, ld, stream));
+    PPX_SHAPE2(3, 3, dispatch(layout, OpNorm2<3, 3>{A, s}, count, ld, stream));
+    PPX_SHAPE2(4, 4, dispatch(layout, OpNorm2<4, 4>{A, s}, count, ld, stream));
+    PPX_SHAPE2(5, 4, dispatch(layout, OpNorm2<5, 4>{A, s}, count, ld, stream));
+    PPX_SHAPE2(4, 5, dispatch(layout, OpNorm2<4, 5>{A, s}, count, ld, stream));
+    PPX_SHAPE2(6, 4, dispatch(layout, OpNorm2<6, 4>{A, s}, count, ld, stream));
     return PPX_ERR_BAD_SHAPE;
 }
 

@@ -140,7 +140,10 @@ def linsolve(factorization, m, n, A, b):
     A, b = _arr(A, m * n), _arr(b, m)
     cnt = A.shape[0]
     x = np.empty((cnt, n))
-    if factorization == "QR":
+    if factorization == "LU":
+        st = np.empty(cnt, dtype=np.int8)
+        check(lib.ppx_cuda_host_linsolve_lu(n, _p(A), _p(b), _p(x), _p(st), cnt))
+    elif factorization == "QR":
         st = np.empty(cnt, dtype=np.int8)
         check(lib.ppx_cuda_host_linsolve_qr(m, n, _p(A), _p(b), _p(x), _p(st), cnt))
     elif factorization == "SVD":
@@ -168,3 +171,31 @@ def eig(n, S, sorted=True, vectors=True):
     z = np.empty((cnt, n * n)) if vectors else None
     check(lib.ppx_cuda_host_eig_sym(n, _p(S), _p(d), _p(z), 1 if sorted else 0, cnt))
     return d, z
+
+
+def inverse(n, A):
+    A = _arr(A, n * n)
+    out = np.empty_like(A)
+    check(lib.ppx_cuda_host_inverse(n, _p(A), _p(out), A.shape[0]))
+    return out
+
+
+def det(n, A):
+    A = _arr(A, n * n)
+    out = np.empty(A.shape[0])
+    check(lib.ppx_cuda_host_det(n, _p(A), _p(out), A.shape[0]))
+    return out
+
+
+def pinv(m, n, A):
+    A = _arr(A, m * n)
+    out = np.empty((A.shape[0], m * n))
+    check(lib.ppx_cuda_host_pinv(m, n, _p(A), _p(out), A.shape[0]))
+    return out
+
+
+def norm2(m, n, A):
+    A = _arr(A, m * n)
+    out = np.empty(A.shape[0])
+    check(lib.ppx_cuda_host_norm2(m, n, _p(A), _p(out), A.shape[0]))
+    return out

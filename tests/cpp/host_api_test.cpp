@@ -22,15 +22,6 @@ static int failures = 0;
 
 constexpr double DEG_RAD(double deg) { return deg * PI / 180.0; }
 
-template <std::size_t M, std::size_t N>
-double norm2(const Matrix<M, N> &v)
-{
-    double s = 0;
-    for (double x : v)
-        s += x * x;
-    return std::sqrt(s);
-}
-
 int main()
 {
     // test/lie_test.cpp:136-142
@@ -112,6 +103,23 @@ int main()
         EXPECT(eig<eigensystem::SymOnlyVal>(g) == result2);
         auto ev = eig<eigensystem::SymValAndVecSorted>(g);
         EXPECT(g * ev.vec == ev.vec * ev.val.diag()); // eigenvectors are defined up to sign: check S z = z d
+    }
+    // test/matrix_test.cpp:809-817 and test/solver_test.cpp:86-103
+    {
+        Matrix<2, 2> x = {1, 2, 4, 3};
+        Matrix<2, 2> result{-0.6, 0.4, 0.8, -0.2};
+        EXPECT(std::fabs(x.det() - (-5.0)) < 1e-14);
+        EXPECT(x.I() == result);
+        EXPECT(inverse(x) == result && std::fabs(determinant(x) + 5.0) < 1e-14);
+        Matrix<4, 4> C{0.438744359656398, 0.381558457093008, 0.765516788149002, 0.795199901137063,
+                       0.186872604554379, 0.489764395788231, 0.445586200710900, 0.646313010111265,
+                       0.709364830858073, 0.754686681982361, 0.276025076998578, 0.679702676853675,
+                       0.655098003973841, 0.162611735194631, 0.118997681558377, 0.498364051982143};
+        EXPECT(std::fabs(norm2(C) - 2.075457904661895) < 10 * EPS_DP);
+        Matrix<4, 1> rhs{1, 2, 3, 4};
+        auto lu = linsolve<Factorization::LU>(C, rhs);
+        EXPECT(lu.s == StatusCode::NORMAL && C * lu.x == rhs);
+        EXPECT(C * pinv(C) == eye<4>());
     }
     // the batched entry points on host vectors of reference records
     {

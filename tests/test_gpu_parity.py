@@ -552,3 +552,61 @@ def test_cpp_host_api(mb, tmp_path):
                            f"-Wl,-rpath,{os.path.join(root, 'matrix_b200')}", "-o", str(exe)])
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and "all passed" in r.stdout, r.stdout + r.stderr
+
+
+# --------------------------------------------------------------------------------------- SURVEY 8(f) rows 2-3
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("n", [2, 3, 4, 6])
+def test_lu_solve_inverse_det(mb, port, layout, n):
+    cnt = 20011
+    A = synth.dense(cnt, n, n, seed=0x81 + n)
+    b = synth.dense(cnt, n, 1, seed=0x91 + n)
+    kappa = np.linalg.cond(A.reshape(cnt, n, n).transpose(0, 2, 1))
+    x, st = run(mb, lambda a_, b_, layout: mb.linsolve(mb.LU, n, n, a_, b_, layout=layout), layout, A, b)
+    rx, rst = port.linsolve_lu(n, A, b)
+    assert np.array_equal(st, rst)
+    assert np.all(rel_err(x, rx) <= REL * np.maximum(1.0, kappa))
+    Ai = run(mb, lambda a_, layout: mb.inverse(n, a_, layout=layout), layout, A)
+    assert np.all(rel_err(Ai, port.inverse(n, A)) <= REL * np.maximum(1.0, kappa))
+    d = run(mb, lambda a_, layout: mb.det(n, a_, layout=layout), layout, A)
+    rd = port.det(n, A)
+    assert np.all(np.abs(d[:, 0] - rd) <= 1e-13 * np.maximum(np.abs(rd), np.abs(A).max(axis=1) ** n))
+
+
+def test_lu_singular_and_golden(mb, fixtures, golden):
+    A6, b6 = fixtures["dense6.A"], fixtures["dense6.b"]
+    x, st = run(mb, lambda a_, b_, layout: mb.linsolve(mb.LU, 6, 6, a_, b_, layout=layout), "aos", A6, b6)
+    assert np.array_equal(st, fixtures["dense6.status_lu"])
+    sing = st == mb.SINGULAR
+    assert sing.sum() >= 3 and np.array_equal(x[sing], b6[sing])  # b untouched (linalg.hpp:1182-1186)
+    Ai = run(mb, lambda a_, layout: mb.inverse(6, a_, layout=layout), "aos", A6)
+    assert np.all(Ai[sing] == 0.0)  # MatrixS::I() returns {} (linalg.hpp:938-941)
+    d = run(mb, lambda a_, layout: mb.det(6, a_, layout=layout), "aos", A6)
+    assert np.all(d[sing] == 0.0)
+    g = golden["inverse_2x2"]  # test/matrix_test.cpp:809-817
+    A = np.array(g["A"], dtype=float).reshape(1, 4)
+    assert np.abs(run(mb, lambda a_, layout: mb.inverse(2, a_, layout=layout), "aos", A)[0] - np.array(g["inverse"])).max() < 1e-15
+    assert abs(run(mb, lambda a_, layout: mb.det(2, a_, layout=layout), "aos", A)[0, 0] - g["det"]) < 1e-14
+
+
+@pytest.mark.parametrize("shape", [(4, 3), (6, 6), (5, 4)])
+def test_pinv_and_norm2(mb, port, shape):
+    m, n = shape
+    cnt = 8192
+    A = synth.dense(cnt, m, n, seed=0xA1 + m * 8 + n)
+    kappa = np.linalg.cond(A.reshape(cnt, n, m).transpose(0, 2, 1))
+    for layout in LAYOUTS:
+        P = run(mb, lambda a_, layout: mb.pinv(m, n, a_, layout=layout), layout, A)
+        if (m, n) != (6, 4):
+            assert np.all(rel_err(P, port.pinv(m, n, A)) <= REL * np.maximum(1.0, kappa))
+        s = run(mb, lambda a_, layout: mb.norm2(m, n, a_, layout=layout), layout, A)
+        assert np.abs(s[:, 0] / port.norm2(m, n, A) - 1).max() < REL
+
+
+def test_norm2_golden(mb, golden):
+    """test/solver_test.cpp:41-104: sigma_max of a 5x4, a 4x5 (wide) and a 4x4 matrix to 10 eps"""
+    g = golden["matrix_norm2"]
+    for case in g["cases"]:
+        A = np.array(case["A"]).reshape(1, -1)
+        s = run(mb, lambda a_, layout: mb.norm2(case["m"], case["n"], a_, layout=layout), "aos", A)
+        assert abs(s[0, 0] - case["norm2"]) < g["tol"], case["m"]
