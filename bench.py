@@ -232,12 +232,15 @@ def main():
     value = world * n * args.steps / (total_ms * 1e-3)
     kernel_ms = statistics.mean(per_step)
     achieved = n * cls.bytes_per_instance() / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    # per-launch DRAM traffic and per-instance fp64 flop counts measured once by ncu on the same seeded workload
+    # (tools/make_counters.py -> profiles/counters.json); null when this n was not profiled
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch_at_n", {}).get(str(n))
+        with open(os.path.join(ROOT, "profiles", "counters.json")) as f:
+            counters = json.load(f)
     except Exception:
-        pass
+        counters = {}
+    c_head = counters.get(args.workload, {})
+    traffic = c_head.get("dram_bytes_per_launch") if c_head.get("instances") == n else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": f"batch_kernel<SOA, {cls.__name__}>",
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_instance": cls.bytes_per_instance(),
@@ -307,10 +310,17 @@ def main():
                     ms, per = time_steps(ww, 5, 3)
                     k_ms = statistics.mean(per)
                     gbs = c.n_default * c.bytes_per_instance() / (k_ms * 1e-3) / 1e9
-                    others.append({"workload": name, "instances": c.n_default, "value": c.n_default / (k_ms * 1e-3),
-                                   "unit": "instances/s", "kernel_ms": k_ms, "hbm_gbs": gbs,
-                                   "hbm_frac": gbs / hbm_peak, "expected_bound": c.bound,
-                                   "algorithmic_bytes_per_instance": c.bytes_per_instance()})
+                    entry = {"workload": name, "instances": c.n_default, "value": c.n_default / (k_ms * 1e-3),
+                             "unit": "instances/s", "kernel_ms": k_ms, "hbm_gbs": gbs,
+                             "hbm_frac": gbs / hbm_peak, "expected_bound": c.bound,
+                             "algorithmic_bytes_per_instance": c.bytes_per_instance()}
+                    cc = counters.get(name, {})
+                    if cc.get("fp64_flops_per_instance") and fp64_peak:
+                        tf = cc["fp64_flops_per_instance"] * entry["value"] / 1e12
+                        entry.update({"fp64_flops_per_instance_ncu": cc["fp64_flops_per_instance"],
+                                      "fp64_tflops": tf, "fp64_frac_of_measured_peak": tf / fp64_peak,
+                                      "fp64_pipe_pct_ncu": cc.get("fp64_pipe_pct")})
+                    others.append(entry)
                     del ww
                     torch.cuda.empty_cache()
                 except Exception as e:  # report, never hide

@@ -53,15 +53,25 @@ struct OpFkJacobian
     const double *q;
     double *T;
     double *Js;
-    template <class IO>
-    __device__ __forceinline__ void operator()(const IO &io) const
+    // measured: prefetching the next tile's joint vector costs the kernel its last registers (spills at 128) and
+    // does not pay -- the kernel is write-dominated (416 of 464 B/instance)
+    static constexpr bool PREFETCH = false;
+    struct In
     {
-        double qi[NJ];
+        double q[NJ];
+    };
+    template <class IO>
+    __device__ __forceinline__ void load(const IO &io, In &in) const
+    {
+        io.load(q, in.q);
+    }
+    template <class IO>
+    __device__ __forceinline__ void compute_store(const IO &io, const In &in) const
+    {
         Rigid t;
-        io.load(q, qi);
         // Jacobian columns stream out (SoA: straight to HBM; AoS: into the warp's staging tile) as they are
         // produced, so the 6 x NJ matrix never occupies registers
-        poe_fk_jacobian<NJ, WANT_T, WANT_J>(ch, qi, t, [&](int col, const double(&v)[6]) {
+        poe_fk_jacobian<NJ, WANT_T, WANT_J>(ch, in.q, t, [&](int col, const double(&v)[6]) {
             io.template put<6 * NJ, 6>(Js, 6 * col, v);
         });
         if (WANT_J)

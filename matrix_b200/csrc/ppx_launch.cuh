@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "../../include/ppx_cuda.h"
@@ -29,6 +30,20 @@ extern std::atomic<uint64_t> g_ppx_launch_count; // util.cu
 namespace ppx_dev
 {
 
+// ops are either a plain functor op(io) or a load / compute_store pair (see batch_kernel_pf)
+template <class Op, class IO>
+__device__ __forceinline__ auto run_tile(const Op &op, const IO &io) -> decltype(op(io))
+{
+    return op(io);
+}
+template <class Op, class IO>
+__device__ __forceinline__ auto run_tile(const Op &op, const IO &io) -> decltype(op.compute_store(io, std::declval<typename Op::In>()))
+{
+    typename Op::In in;
+    op.load(io, in);
+    op.compute_store(io, in);
+}
+
 template <int LAYOUT, class Op>
 __global__ void __launch_bounds__(Op::BLOCK, Op::MINB) batch_kernel(const __grid_constant__ Op op, size_t n, size_t ld)
 {
@@ -37,8 +52,63 @@ __global__ void __launch_bounds__(Op::BLOCK, Op::MINB) batch_kernel(const __grid
     for (size_t base = (size_t)blockIdx.x * Op::BLOCK; base < n; base += stride)
     {
         TileIO<LAYOUT> io(base, n, ld, ppx_smem, Op::MAXW);
-        op(io);
+        run_tile(op, io);
     }
+}
+
+// Software-pipelined variant for ops that split into load(io, in) / compute_store(io, in): the inputs of tile k+1
+// are requested before tile k is computed, so the DRAM read latency of a tile is hidden behind the arithmetic of
+// the previous one instead of being exposed once per tile (ncu: `long_scoreboard` was the top stall of the
+// kinematics kernel at 16 warps/SM).
+template <int LAYOUT, class Op>
+__global__ void __launch_bounds__(Op::BLOCK, Op::MINB) batch_kernel_pf(const __grid_constant__ Op op, size_t n, size_t ld)
+{
+    extern __shared__ __align__(16) double ppx_smem[];
+    const size_t stride = (size_t)gridDim.x * Op::BLOCK;
+    size_t base = (size_t)blockIdx.x * Op::BLOCK;
+    if (base >= n)
+        return;
+    typename Op::In cur, nxt;
+    {
+        TileIO<LAYOUT> io(base, n, ld, ppx_smem, Op::MAXW);
+        op.load(io, cur);
+    }
+    for (;;)
+    {
+        const size_t next = base + stride;
+        const bool more = next < n;
+        if (more)
+        {
+            TileIO<LAYOUT> ion(next, n, ld, ppx_smem, Op::MAXW);
+            op.load(ion, nxt);
+        }
+        TileIO<LAYOUT> io(base, n, ld, ppx_smem, Op::MAXW);
+        op.compute_store(io, cur);
+        if (!more)
+            break;
+        cur = nxt;
+        base = next;
+    }
+}
+
+template <class Op, class = void>
+struct has_prefetch : std::false_type
+{
+};
+template <class Op>
+struct has_prefetch<Op, typename std::enable_if<Op::PREFETCH>::type> : std::true_type
+{
+};
+
+template <int LAYOUT, class Op>
+typename std::enable_if<has_prefetch<Op>::value, void (*)(const Op, size_t, size_t)>::type pick_kernel()
+{
+    return batch_kernel_pf<LAYOUT, Op>;
+}
+template <int LAYOUT, class Op>
+typename std::enable_if<!has_prefetch<Op>::value, void (*)(const Op, size_t, size_t)>::type pick_kernel()
+{
+    return batch_kernel<LAYOUT, Op>;
 }
 
 struct DeviceInfo
@@ -82,7 +152,7 @@ int launch(const Op &op, size_t n, size_t ld, void *stream)
     int rc = device_info(info, device);
     if (rc != PPX_OK)
         return rc;
-    auto kern = batch_kernel<LAYOUT, Op>;
+    auto kern = pick_kernel<LAYOUT, Op>();
     const size_t smem = TileIO<LAYOUT>::smem_bytes(Op::BLOCK, Op::MAXW);
     static int blocks_per_sm[64]; // per instantiation, per device
     if (blocks_per_sm[device] == 0)

@@ -68,6 +68,20 @@ class Ur5FkJacobian(Workload):
 
 
 
+class Ur5FkJacobianAoS(Ur5FkJacobian):
+    """config 2 on the drop-in layout: device-resident arrays of dense reference records (std::vector<MatrixS>)"""
+    name = "ur5_fk_jacobian_aos"
+
+    def setup(self):
+        self.kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
+        self.q = _device_records(self.n, 6, synth.SEEDS["ur5_fk_jacobian"], self.first, -np.pi, np.pi, self.device)
+        self.T = torch.empty((self.n, 16), dtype=torch.float64, device=self.device)
+        self.Js = torch.empty((self.n, 36), dtype=torch.float64, device=self.device)
+
+    def step(self):
+        self.kin.fk_jacobian(self.q, layout=mb.AOS, out_T=self.T, out_Js=self.Js)
+
+
 class Se3ExpLog(Workload):
     """config 1: se3::exp -> SE3::log round trip, fused"""
     name = "se3_exp_log"
@@ -188,4 +202,4 @@ class IkNewtonStep(Workload):
 
 
 
-WORKLOADS = {w.name: w for w in (Ur5FkJacobian, Se3ExpLog, LinsolveQR43, Svd66, EigSym4, IkNewtonStep)}
+WORKLOADS = {w.name: w for w in (Ur5FkJacobian, Ur5FkJacobianAoS, Se3ExpLog, LinsolveQR43, Svd66, EigSym4, IkNewtonStep)}

@@ -6,6 +6,7 @@ HEADLINE = "ur5_fk_jacobian"
 # 16-core host (the CPU throughput does not depend on the batch size)
 META = {
     "ur5_fk_jacobian": {"cpu_sample": 1 << 22},
+    "ur5_fk_jacobian_aos": {"cpu_sample": 1 << 22},
     "se3_exp_log": {"cpu_sample": 1 << 24},
     "linsolve_qr_4x3": {"cpu_sample": 1 << 25},
     "svd_6x6": {"cpu_sample": 1 << 22},
