@@ -20,7 +20,7 @@ SIZES = {"ur5_fk_jacobian": 1 << 24, "ur5_fk_jacobian_aos": 1 << 24, "se3_exp_lo
          "svd_6x6": 1 << 24, "eig_sym_4": 1 << 24, "ik_newton_step": 1 << 25}
 out = {}
 for path in sys.argv[1:]:
-    m = re.search(r"prof_[^_]+_(.+)\.ncu-rep$", os.path.basename(path))
+    m = re.search(r"prof_[^_]+_(.+?)\.(?:ncu-rep|raw\.csv)$", os.path.basename(path))
     wl = m.group(1)
     s = summarise(path)[0]
     n = SIZES[wl]

@@ -37,8 +37,15 @@ UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1.0, "us": 
         "Ghz": 1e3, "Mhz": 1.0, "cycle/nsecond": 1e3, "cycle/usecond": 1.0}
 
 
+def raw_csv(path):
+    """raw counter page of a report: either an .ncu-rep (read through ncu -i) or an already exported .raw.csv"""
+    if path.endswith(".csv"):
+        return open(path).read()
+    return subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+
+
 def summarise(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = raw_csv(path)
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     res = []
@@ -70,7 +77,7 @@ def summarise(path):
 
 def stall_table(path, top=8):
     """per-warp-state sampling percentages for the (single) kernel in the report"""
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = raw_csv(path)
     rows = list(csv.reader(io.StringIO(out)))
     hdr, vals = rows[0], rows[2]
     st = {}
