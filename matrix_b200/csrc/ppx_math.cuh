@@ -589,6 +589,47 @@ PPX_DEV bool lu_factor_solve(double (&A)[N * N], double (&B)[N * (NRHS > 0 ? NRH
 }
 
 // ------------------------------------------------------------------------------------------------
+// Exact power-of-two pre-scaling for the Jacobi solvers, done entirely on the integer pipe (which is idle in these
+// fp64-bound kernels).  The rotation formulas square differences of squared norms, i.e. they need |a|^4 to be
+// representable; the reference's Householder steps divide by a running scale first (linalg.hpp:628-637, 982-996)
+// and take any magnitude.  Subtracting `shift` from every exponent field brings the largest entry into [1, 2)
+// exactly; entries more than 2^1022 below it flush to zero.  Results are scaled back the same way.
+template <int L>
+PPX_DEV int pow2_shift(const double (&a)[L])
+{
+    int m = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++)
+        m = max(m, __double2hiint(a[i]) & 0x7ff00000);
+    // zero / denormal-only matrices and inf / NaN are left alone
+    const int shift = (m == 0 || m == 0x7ff00000) ? 0 : (m >> 20) - 1023;
+    // only magnitudes whose fourth power leaves the fp64 range need the treatment; the decision is taken per warp
+    // so that the rescaling code is skipped (warp-uniformly) for ordinary data
+    const bool need = shift > 200 || shift < -200;
+    return __any_sync(0xffffffffu, need) ? shift : 0;
+}
+PPX_DEV double pow2_mul(double x, int shift) // x * 2^-shift for |shift| <= 1022, exponent arithmetic only
+{
+    const int hi = __double2hiint(x);
+    const int f = (hi >> 20) & 0x7ff;
+    const int nf = f - shift;
+    const bool keep = f == 0 || f == 0x7ff; // zero, denormal, inf, NaN
+    const int nhi = nf <= 0 ? (hi & 0x80000000) : (nf >= 0x7ff ? ((hi & 0x80000000) | 0x7ff00000) : hi - (shift << 20));
+    const int nlo = (nf <= 0 || nf >= 0x7ff) ? 0 : __double2loint(x);
+    return keep ? x : __hiloint2double(nhi, nlo);
+}
+
+template <int L>
+PPX_DEV void pow2_rescale(double (&a)[L], int shift) // one warp-uniform branch around the whole array
+{
+    if (shift != 0)
+    {
+#pragma unroll
+        for (int i = 0; i < L; i++)
+            a[i] = pow2_mul(a[i], shift);
+    }
+}
+
 // Branch-free reciprocal square root / reciprocal: the hardware seed (MUFU.RSQ64H / MUFU.RCP64H, relative
 // error ~2^-22) refined by one third-order step, full fp64 accuracy for normal, non-zero arguments.  Unlike
 // sqrt() and operator/ there is no special-case slow path, hence no call and no convergence barrier in the
@@ -850,12 +891,18 @@ PPX_DEV void jacobi_eig_sym(const double (&S)[N * N], bool sorted, double (&d)[N
 {
     double a[N * N]; // only the entries sym_ix() maps to are live
     double fro2 = 0.0;
+    const int shift = pow2_shift(S);
+    double Ss[N * N];
+#pragma unroll
+    for (int i = 0; i < N * N; i++)
+        Ss[i] = S[i];
+    pow2_rescale(Ss, shift);
 #pragma unroll
     for (int c = 0; c < N; c++)
 #pragma unroll
         for (int r = c; r < N; r++)
         {
-            const double v = S[r + c * N]; // lower triangle, as tred2 reads it
+            const double v = Ss[r + c * N]; // lower triangle, as tred2 reads it
             a[sym_ix(r, c, N)] = v;
             fro2 = fma(r == c ? v : 2.0 * v, v, fro2);
         }
@@ -935,6 +982,7 @@ PPX_DEV void jacobi_eig_sym(const double (&S)[N * N], bool sorted, double (&d)[N
 #pragma unroll
     for (int i = 0; i < N; i++)
         d[i] = a[i + i * N];
+    pow2_rescale(d, -shift);
     if (sorted)
     {
         // ascending selection sort with compile-time indices (eigsrt swaps whole columns)

@@ -52,19 +52,23 @@ struct OpSVD
     {
         double a[M * N], v[N * N], w2[N], sv[N];
         io.load(A, a);
+        const int shift = pow2_shift(a);
+        pow2_rescale(a, shift);
         jacobi_svd_core<M, N, WANT_V>(a, v, w2);
 #pragma unroll
         for (int j = 0; j < N; j++)
         {
-            sv[j] = sqrt(w2[j]);
+            const double ws = sqrt(w2[j]);
+            sv[j] = ws;
             if (WANT_U)
             {
-                const double inv = sv[j] > 0.0 ? 1.0 / sv[j] : 0.0;
+                const double inv = ws > 0.0 ? 1.0 / ws : 0.0;
 #pragma unroll
                 for (int i = 0; i < M; i++)
                     a[i + j * M] *= inv;
             }
         }
+        pow2_rescale(sv, -shift);
         if (WANT_U)
             io.store(U, a);
         io.store(w, sv);
@@ -86,8 +90,11 @@ struct OpLinsolveSVD
         double a[M * N], v[N * N], w2[N], rhs[M], sol[N];
         io.load(A, a);
         io.load(b, rhs);
+        const int shift = pow2_shift(a);
+        pow2_rescale(a, shift);
         jacobi_svd_core<M, N, true>(a, v, w2);
         jacobi_svd_solve<M, N>(a, v, w2, rhs, sol);
+        pow2_rescale(sol, shift); // (A 2^-shift)^+ b = 2^shift A^+ b
         io.store(x, sol);
     }
 };
@@ -200,6 +207,8 @@ struct OpPinv
     {
         double a[M * N], v[N * N], w2[N], p[N * M];
         io.load(A, a);
+        const int shift = pow2_shift(a);
+        pow2_rescale(a, shift);
         jacobi_svd_core<M, N, true>(a, v, w2);
         double wmax2 = w2[0];
 #pragma unroll
@@ -224,6 +233,7 @@ struct OpPinv
                     p[r + c * N] = fma(v[r + j * N], t, p[r + c * N]);
             }
         }
+        pow2_rescale(p, shift); // (A 2^-shift)^+ = 2^shift A^+
         io.store(P, p);
     }
 };
@@ -241,6 +251,8 @@ struct OpNorm2
     {
         double a[M * N], t[R * C], v[C * C], w2[C];
         io.load(A, a);
+        const int shift = pow2_shift(a);
+        pow2_rescale(a, shift);
 #pragma unroll
         for (int c = 0; c < C; c++)
 #pragma unroll
@@ -251,7 +263,8 @@ struct OpNorm2
 #pragma unroll
         for (int j = 1; j < C; j++)
             wmax2 = fmax(wmax2, w2[j]);
-        const double out[1] = {sqrt(wmax2)};
+        double out[1] = {sqrt(wmax2)};
+        pow2_rescale(out, -shift);
         io.store(s, out);
     }
 };

@@ -610,3 +610,25 @@ def test_norm2_golden(mb, golden):
         A = np.array(case["A"]).reshape(1, -1)
         s = run(mb, lambda a_, layout: mb.norm2(case["m"], case["n"], a_, layout=layout), "aos", A)
         assert abs(s[0, 0] - case["norm2"]) < g["tol"], case["m"]
+
+
+@pytest.mark.parametrize("scale", [1e-250, 1e-100, 1e-9, 1e9, 1e100, 1e250])
+def test_svd_eig_scale_with_their_input(mb, port, scale):
+    """The Jacobi path pre-scales by an exact power of two (integer exponent arithmetic), so singular values and
+    eigenvalues scale exactly with the input at any magnitude.  The reference is compared where it is itself valid:
+    its absolute EPS_DP tests (linalg.hpp:863, 1105) break it for small inputs and its unscaled f*f + h*h
+    (:803, 846) overflows for large ones."""
+    A = synth.dense(2048, 6, 6, seed=0xC1)
+    _, w1, _ = run(mb, lambda a_, layout: mb.svdcmp(6, 6, a_, layout=layout), "soa", A)
+    _, w2, _ = run(mb, lambda a_, layout: mb.svdcmp(6, 6, a_, layout=layout), "soa", A * scale)
+    assert np.all(np.isfinite(w2))
+    assert np.all(np.abs(np.sort(w2, axis=1) / scale - np.sort(w1, axis=1)).max(axis=1) / w1.max(axis=1) < 1e-13)
+    S = synth.symmetric(2048, 4, seed=0xC3)
+    d1, _ = run(mb, lambda s_, layout: mb.eig(4, s_, layout=layout), "soa", S)
+    d2, _ = run(mb, lambda s_, layout: mb.eig(4, s_, layout=layout), "soa", S * scale)
+    assert np.all(np.isfinite(d2)) and np.abs(d2 / scale - d1).max() < 1e-13
+    if 1e-3 <= scale <= 1e100:
+        _, rw, _ = port.svd(6, 6, A * scale)
+        assert np.all(np.abs(np.sort(w2, axis=1) - np.sort(rw, axis=1)).max(axis=1) / rw.max(axis=1) < REL)
+        rd, _ = port.eig_sym(4, S * scale, True)
+        assert np.all(np.abs(d2 - rd).max(axis=1) / np.abs(rd).max(axis=1) < REL)
