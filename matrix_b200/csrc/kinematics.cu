@@ -53,25 +53,22 @@ struct OpFkJacobian
     const double *q;
     double *T;
     double *Js;
-    // measured: prefetching the next tile's joint vector costs the kernel its last registers (spills at 128) and
-    // does not pay -- the kernel is write-dominated (416 of 464 B/instance)
-    static constexpr bool PREFETCH = false;
-    struct In
-    {
-        double q[NJ];
-    };
+    static constexpr bool PREFETCH = true;
+    static constexpr int IN_WIDTH = NJ;
     template <class IO>
-    __device__ __forceinline__ void load(const IO &io, In &in) const
+    __device__ __forceinline__ void prefetch(const IO &io, double *stage) const
     {
-        io.load(q, in.q);
+        io.template async_load<NJ>(q, stage);
     }
     template <class IO>
-    __device__ __forceinline__ void compute_store(const IO &io, const In &in) const
+    __device__ __forceinline__ void compute_store(const IO &io, const double *stage) const
     {
+        double qi[NJ];
+        io.template read_staged<NJ>(stage, qi);
         Rigid t;
         // Jacobian columns stream out (SoA: straight to HBM; AoS: into the warp's staging tile) as they are
         // produced, so the 6 x NJ matrix never occupies registers
-        poe_fk_jacobian<NJ, WANT_T, WANT_J>(ch, in.q, t, [&](int col, const double(&v)[6]) {
+        poe_fk_jacobian<NJ, WANT_T, WANT_J>(ch, qi, t, [&](int col, const double(&v)[6]) {
             io.template put<6 * NJ, 6>(Js, 6 * col, v);
         });
         if (WANT_J)

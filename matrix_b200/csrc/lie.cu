@@ -80,22 +80,20 @@ struct OpSe3ExpLog
     static constexpr int BLOCK = 256, MINB = 3, MAXW = 6;
     const double *xi;
     double *xo;
-    static constexpr bool PREFETCH = true; // 82.6 % -> 88.9 % of the HBM roofline
-    struct In
-    {
-        double x[6];
-    };
+    static constexpr bool PREFETCH = true; // 82.6 % -> 88 % of the copy roofline
+    static constexpr int IN_WIDTH = 6;
     template <class IO>
-    __device__ __forceinline__ void load(const IO &io, In &in) const
+    __device__ __forceinline__ void prefetch(const IO &io, double *stage) const
     {
-        io.load(xi, in.x);
+        io.template async_load<6>(xi, stage);
     }
     template <class IO>
-    __device__ __forceinline__ void compute_store(const IO &io, const In &in) const
+    __device__ __forceinline__ void compute_store(const IO &io, const double *stage) const
     {
-        double y[6];
+        double x[6], y[6];
+        io.template read_staged<6>(stage, x);
         Rigid t;
-        se3_exp(in.x, t);
+        se3_exp(x, t);
         SE3_log(t, y);
         io.store(xo, y);
     }

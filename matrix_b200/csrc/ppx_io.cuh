@@ -22,6 +22,16 @@ namespace ppx_dev
 constexpr int LAYOUT_AOS = 0;
 constexpr int LAYOUT_SOA = 1;
 
+// cp.async (LDGSTS): global -> shared without passing through registers, 8 bytes per request
+__device__ __forceinline__ void cp_async_8(double *smem_dst, const double *gmem_src)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
 template <int LAYOUT>
 struct TileIO;
 
@@ -32,7 +42,7 @@ struct TileIO<LAYOUT_SOA>
     size_t ld;  // component stride
     bool valid; // i < n
 
-    static constexpr size_t smem_bytes(int /*block*/, int /*max_width*/) { return 0; }
+    __host__ __device__ static constexpr size_t smem_bytes(int /*block*/, int /*max_width*/) { return 0; }
 
     __device__ __forceinline__ TileIO(size_t tile_base, size_t n, size_t ld_, double * /*smem*/, int /*max_width*/)
         : i(tile_base + threadIdx.x), ld(ld_), valid(tile_base + threadIdx.x < n) {}
@@ -70,6 +80,27 @@ struct TileIO<LAYOUT_SOA>
 
     template <int D>
     __device__ __forceinline__ void flush(double *__restrict__ /*base*/) const {}
+
+    // asynchronous input staging: this thread's D components go to stage[k*blockDim + tid] and are read back by
+    // the same thread after cp_async_wait (no block-level synchronisation needed)
+    __host__ __device__ static constexpr size_t stage_doubles(int block, int width) { return (size_t)block * width; }
+    template <int D>
+    __device__ __forceinline__ void async_load(const double *__restrict__ base, double *stage) const
+    {
+        if (valid)
+        {
+#pragma unroll
+            for (int k = 0; k < D; k++)
+                cp_async_8(stage + k * blockDim.x + threadIdx.x, base + (size_t)k * ld + i);
+        }
+    }
+    template <int D>
+    __device__ __forceinline__ void read_staged(const double *stage, double (&r)[D]) const
+    {
+#pragma unroll
+        for (int k = 0; k < D; k++)
+            r[k] = valid ? stage[k * blockDim.x + threadIdx.x] : 0.0;
+    }
 };
 
 template <>
@@ -82,7 +113,7 @@ struct TileIO<LAYOUT_AOS>
     bool valid;
     double *ws;   // this warp's staging tile: 32 records, stride (max_width | 1) doubles
 
-    static constexpr size_t smem_bytes(int block, int max_width)
+    __host__ __device__ static constexpr size_t smem_bytes(int block, int max_width)
     {
         return (size_t)(block / 32) * 32 * (size_t)(max_width | 1) * sizeof(double);
     }
@@ -157,6 +188,38 @@ struct TileIO<LAYOUT_AOS>
             }
         }
         __syncwarp();
+    }
+
+    // asynchronous input staging: the warp's contiguous span goes, element by element, into a padded tile of the
+    // stage buffer; read_staged() is the per-thread side after cp_async_wait + __syncwarp
+    __host__ __device__ static constexpr size_t stage_doubles(int block, int width) { return (size_t)block * (width | 1); }
+    template <int D>
+    __device__ __forceinline__ void async_load(const double *__restrict__ base, double *stage) const
+    {
+        constexpr int DP = D | 1;
+        double *tile = stage + (size_t)(threadIdx.x >> 5) * 32 * DP;
+        const double *src = base + i0 * D;
+        const int total = nvalid * D;
+#pragma unroll
+        for (int m = 0; m < D; m++)
+        {
+            const int j = lane + 32 * m;
+            if (j < total)
+            {
+                const int rec = j / D;
+                cp_async_8(tile + rec * DP + (j - rec * D), src + j);
+            }
+        }
+    }
+    template <int D>
+    __device__ __forceinline__ void read_staged(const double *stage, double (&r)[D]) const
+    {
+        constexpr int DP = D | 1;
+        const double *tile = stage + (size_t)(threadIdx.x >> 5) * 32 * DP;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < D; k++)
+            r[k] = valid ? tile[lane * DP + k] : 0.0;
     }
 };
 

@@ -30,20 +30,6 @@ extern std::atomic<uint64_t> g_ppx_launch_count; // util.cu
 namespace ppx_dev
 {
 
-// ops are either a plain functor op(io) or a load / compute_store pair (see batch_kernel_pf)
-template <class Op, class IO>
-__device__ __forceinline__ auto run_tile(const Op &op, const IO &io) -> decltype(op(io))
-{
-    return op(io);
-}
-template <class Op, class IO>
-__device__ __forceinline__ auto run_tile(const Op &op, const IO &io) -> decltype(op.compute_store(io, std::declval<typename Op::In>()))
-{
-    typename Op::In in;
-    op.load(io, in);
-    op.compute_store(io, in);
-}
-
 template <int LAYOUT, class Op>
 __global__ void __launch_bounds__(Op::BLOCK, Op::MINB) batch_kernel(const __grid_constant__ Op op, size_t n, size_t ld)
 {
@@ -52,26 +38,31 @@ __global__ void __launch_bounds__(Op::BLOCK, Op::MINB) batch_kernel(const __grid
     for (size_t base = (size_t)blockIdx.x * Op::BLOCK; base < n; base += stride)
     {
         TileIO<LAYOUT> io(base, n, ld, ppx_smem, Op::MAXW);
-        run_tile(op, io);
+        op(io);
     }
 }
 
-// Software-pipelined variant for ops that split into load(io, in) / compute_store(io, in): the inputs of tile k+1
-// are requested before tile k is computed, so the DRAM read latency of a tile is hidden behind the arithmetic of
-// the previous one instead of being exposed once per tile (ncu: `long_scoreboard` was the top stall of the
-// kinematics kernel at 16 warps/SM).
+// Software-pipelined variant for ops that declare PREFETCH: the inputs of tile k+1 are requested with cp.async into
+// a double-buffered shared-memory stage before tile k is computed, so the DRAM read latency of a tile is hidden
+// behind the arithmetic of the previous one without holding any registers (a register prefetch made the
+// 128-register kinematics kernel spill).  ncu on the unstaged kernel: 40 % of all warp samples sat in
+// `long_scoreboard` on the first use of the freshly loaded joint angles.
+// Op interface: IN_WIDTH (doubles per instance), prefetch(io, stage), compute_store(io, stage).
 template <int LAYOUT, class Op>
 __global__ void __launch_bounds__(Op::BLOCK, Op::MINB) batch_kernel_pf(const __grid_constant__ Op op, size_t n, size_t ld)
 {
     extern __shared__ __align__(16) double ppx_smem[];
+    constexpr size_t STAGE = TileIO<LAYOUT>::stage_doubles(Op::BLOCK, Op::IN_WIDTH);
+    double *stage = ppx_smem + TileIO<LAYOUT>::smem_bytes(Op::BLOCK, Op::MAXW) / sizeof(double);
     const size_t stride = (size_t)gridDim.x * Op::BLOCK;
     size_t base = (size_t)blockIdx.x * Op::BLOCK;
     if (base >= n)
         return;
-    typename Op::In cur, nxt;
+    int buf = 0;
     {
         TileIO<LAYOUT> io(base, n, ld, ppx_smem, Op::MAXW);
-        op.load(io, cur);
+        op.prefetch(io, stage);
+        cp_async_commit();
     }
     for (;;)
     {
@@ -80,13 +71,15 @@ __global__ void __launch_bounds__(Op::BLOCK, Op::MINB) batch_kernel_pf(const __g
         if (more)
         {
             TileIO<LAYOUT> ion(next, n, ld, ppx_smem, Op::MAXW);
-            op.load(ion, nxt);
+            op.prefetch(ion, stage + (buf ^ 1) * STAGE);
         }
+        cp_async_commit();
+        cp_async_wait<1>(); // everything but the group just committed has landed: this tile's inputs
         TileIO<LAYOUT> io(base, n, ld, ppx_smem, Op::MAXW);
-        op.compute_store(io, cur);
+        op.compute_store(io, stage + buf * STAGE);
         if (!more)
             break;
-        cur = nxt;
+        buf ^= 1;
         base = next;
     }
 }
@@ -99,6 +92,17 @@ template <class Op>
 struct has_prefetch<Op, typename std::enable_if<Op::PREFETCH>::type> : std::true_type
 {
 };
+
+template <int LAYOUT, class Op>
+constexpr typename std::enable_if<has_prefetch<Op>::value, size_t>::type stage_bytes()
+{
+    return 2 * TileIO<LAYOUT>::stage_doubles(Op::BLOCK, Op::IN_WIDTH) * sizeof(double);
+}
+template <int LAYOUT, class Op>
+constexpr typename std::enable_if<!has_prefetch<Op>::value, size_t>::type stage_bytes()
+{
+    return 0;
+}
 
 template <int LAYOUT, class Op>
 typename std::enable_if<has_prefetch<Op>::value, void (*)(const Op, size_t, size_t)>::type pick_kernel()
@@ -153,7 +157,7 @@ int launch(const Op &op, size_t n, size_t ld, void *stream)
     if (rc != PPX_OK)
         return rc;
     auto kern = pick_kernel<LAYOUT, Op>();
-    const size_t smem = TileIO<LAYOUT>::smem_bytes(Op::BLOCK, Op::MAXW);
+    const size_t smem = TileIO<LAYOUT>::smem_bytes(Op::BLOCK, Op::MAXW) + stage_bytes<LAYOUT, Op>();
     static int blocks_per_sm[64]; // per instantiation, per device
     if (blocks_per_sm[device] == 0)
     {
