@@ -105,6 +105,19 @@ def cpu_ik_newton_step(oracle, n, first=0):
 
 
 
+def cpu_inverse_space_codo(oracle, n, first=0):
+    S = np.ascontiguousarray(synth.UR5_SCREWS)
+    M = np.ascontiguousarray(synth.UR5_HOME)
+    q = synth.joint_angles(n, first=first, seed=synth.SEEDS["ik_newton_step"]) * 0.95
+    Tt = oracle.poe_fk_jacobian(S, M, q, want_Js=False)[0]
+    q0 = q - 0.05
+    lo, hi = -np.pi * np.ones(6), np.pi * np.ones(6)
+    qo = np.empty((n, 6))
+    _touch(qo)
+    return lambda: _ok(oracle.lib.ppxo_ik_codo(_d(S), _d(M), C.c_int(6), _d(lo), _d(hi), _d(Tt), _d(q0), _d(qo), None,
+                                               None, None, C.c_size_t(n), C.c_int(NTHREADS)))
+
+
 CPU = {
     "ur5_fk_jacobian": cpu_ur5_fk_jacobian,
     "ur5_fk_jacobian_aos": cpu_ur5_fk_jacobian,
@@ -113,4 +126,5 @@ CPU = {
     "svd_6x6": cpu_svd_6x6,
     "eig_sym_4": cpu_eig_sym_4,
     "ik_newton_step": cpu_ik_newton_step,
+    "inverse_space_codo": cpu_inverse_space_codo,
 }

@@ -618,8 +618,25 @@ public:
         cuda::check(ppx_cuda_host_poe_fk_jacobian(s.data(), home().data(), (int)N, q.data(), nullptr, J.data(), 1));
         return J;
     }
-    // Newton-SVD loop of test/lie_test.cpp:96-113 (the demo's CoDo trust-region variant is out of scope)
-    Q inverseSpace(const SE3 &pose, Q init, int max_iter = 20) const
+    // bounded trust-region dogleg (details::CoDo) with the joints' ranges, demo/robotics.hpp:126-152:
+    // the optimiser's result if it converged, else init
+    Q inverseSpace(const SE3 &pose, const Q &init) const
+    {
+        static_assert(N == 6, "CoDo<N,6> needs a square Jacobian (linsolve<LU>, optimization.hpp:608)");
+        Q q;
+        auto s = screws();
+        double lo[N], hi[N];
+        for (std::size_t i = 0; i < N; i++)
+        {
+            lo[i] = JList[i].range.first;
+            hi[i] = JList[i].range.second;
+        }
+        cuda::check(ppx_cuda_host_ik_codo(s.data(), home().data(), (int)N, lo, hi, pose.data(), init.data(), q.data(),
+                                          nullptr, nullptr, nullptr, 1));
+        return q;
+    }
+    // Newton-SVD loop of the test suite's private kinematics copy, test/lie_test.cpp:96-113
+    Q inverseSpaceNewton(const SE3 &pose, Q init, int max_iter = 20) const
     {
         Q q;
         auto s = screws();
@@ -676,10 +693,27 @@ void batch_ik_newton_step(const kinematics<N> &kin, const Matrix<N, 1> *q, const
     auto s = kin.screws();
     check(ppx_cuda_host_ik_newton_step(s.data(), kin.home().data(), (int)N, dp(q), dp(target), dp(q_out), dp(Vs), n));
 }
-// the whole Newton loop per instance; iters / status may be null
+// kinematics<6>::inverseSpace (CoDo trust region, joint ranges as the box) per instance; status may be null
 template <std::size_t N>
 void batch_inverseSpace(const kinematics<N> &kin, const SE3 *target, const Matrix<N, 1> *init, Matrix<N, 1> *q_out,
-                        std::size_t n, int max_iter = 20, int32_t *iters = nullptr, StatusCode *status = nullptr)
+                        std::size_t n, StatusCode *status = nullptr)
+{
+    static_assert(N == 6, "CoDo<N,6> needs a square Jacobian");
+    auto s = kin.screws();
+    double lo[N], hi[N];
+    for (std::size_t i = 0; i < N; i++)
+    {
+        lo[i] = kin.JointList()[i].range.first;
+        hi[i] = kin.JointList()[i].range.second;
+    }
+    check(ppx_cuda_host_ik_codo(s.data(), kin.home().data(), (int)N, lo, hi, dp(target), dp(init), dp(q_out), nullptr,
+                                nullptr, reinterpret_cast<int8_t *>(status), n));
+}
+// the whole Newton-SVD loop of test/lie_test.cpp:96-113 per instance; iters / status may be null
+template <std::size_t N>
+void batch_inverseSpaceNewton(const kinematics<N> &kin, const SE3 *target, const Matrix<N, 1> *init,
+                              Matrix<N, 1> *q_out, std::size_t n, int max_iter = 20, int32_t *iters = nullptr,
+                              StatusCode *status = nullptr)
 {
     auto s = kin.screws();
     check(ppx_cuda_host_ik_solve(s.data(), kin.home().data(), (int)N, dp(init), dp(target), max_iter, dp(q_out), iters,

@@ -122,6 +122,15 @@ int ppx_cuda_batch_ik_solve(const double *screws, const double *home, int njoint
                             const double *Ttarget, int max_iter, double *q_out, int32_t *iters, int8_t *status,
                             size_t n, int layout, size_t ld, void *stream);
 
+/* kinematics<6>::inverseSpace(pose, init) of demo/robotics.hpp:126-152: the bounded trust-region dogleg
+ * details::CoDo<6,6> (include/optimization.hpp:497-829) on f(q) = log(T(q) pose^-1) with the joints' ranges lo/hi
+ * (HOST pointers, njoints each) as the box.  q_out = the optimiser's result if CONVERGED, else init (what inverseSpace
+ * returns).  Optional outputs: x_raw (last iterate, njoints), fnorm (OptResult::y = 0.5 |f|, dense double[n]),
+ * status (int8 dense: CONVERGED / DIVERGED). */
+int ppx_cuda_batch_ik_codo(const double *screws, const double *home, int njoints, const double *lo, const double *hi,
+                           const double *Ttarget, const double *init, double *q_out, double *x_raw, double *fnorm,
+                           int8_t *status, size_t n, int layout, size_t ld, void *stream);
+
 /* ---- dense factorisations (include/linalg.hpp) --------------------------------------------- */
 /* linsolve<Factorization::QR>(A, b), :535-603, 1189-1200.  A: m*n, b: m -> x: n, status: int8 dense [n_inst]
  * (may be NULL).  On SINGULAR x = first n entries of b, as in the reference. */
@@ -174,6 +183,9 @@ int ppx_cuda_host_ik_newton_step(const double *screws, const double *home, int n
 int ppx_cuda_host_ik_solve(const double *screws, const double *home, int njoints, const double *q0,
                            const double *Ttarget, int max_iter, double *q_out, int32_t *iters, int8_t *status,
                            size_t n);
+int ppx_cuda_host_ik_codo(const double *screws, const double *home, int njoints, const double *lo, const double *hi,
+                          const double *Ttarget, const double *init, double *q_out, double *x_raw, double *fnorm,
+                          int8_t *status, size_t n);
 int ppx_cuda_host_linsolve_qr(int m, int n, const double *A, const double *b, double *x, int8_t *status,
                               size_t count);
 int ppx_cuda_host_svd(int m, int n, const double *A, double *U, double *w, double *V, size_t count);

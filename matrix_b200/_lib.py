@@ -54,6 +54,7 @@ _SIGNATURES = {
     "ppx_cuda_batch_poe_fk_jacobian": [_vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_batch_ik_newton_step": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_batch_ik_solve": [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _sz, _vp],
+    "ppx_cuda_batch_ik_codo": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_batch_linsolve_qr": [_i, _i, _vp, _vp, _vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_batch_svd": [_i, _i, _vp, _vp, _vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_batch_linsolve_svd": [_i, _i, _vp, _vp, _vp, _sz, _i, _sz, _vp],
@@ -76,6 +77,7 @@ _SIGNATURES = {
     "ppx_cuda_host_poe_fk_jacobian": [_vp, _vp, _i, _vp, _vp, _vp, _sz],
     "ppx_cuda_host_ik_newton_step": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _sz],
     "ppx_cuda_host_ik_solve": [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz],
+    "ppx_cuda_host_ik_codo": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz],
     "ppx_cuda_host_linsolve_qr": [_i, _i, _vp, _vp, _vp, _vp, _sz],
     "ppx_cuda_host_svd": [_i, _i, _vp, _vp, _vp, _vp, _sz],
     "ppx_cuda_host_linsolve_svd": [_i, _i, _vp, _vp, _vp, _sz],

@@ -177,8 +177,29 @@ class Kinematics:
             check(lib.ppx_cuda_batch_ik_newton_step(self._ps, self._ph, nj, pq, pt, pqo, pV, n, layout, ld, _stream()))
         return (qo, Vs) if want_Vs else qo
 
-    def inverseSpace(self, Ttarget, init, max_iter=20, layout=AOS, n=None):
-        """the Newton loop of test/lie_test.cpp:96-113 -> (q, iterations int32[n], status int8[n])"""
+    def inverseSpace(self, Ttarget, init, lo=None, hi=None, layout=AOS, n=None):
+        """kinematics<6>::inverseSpace(pose, init), demo/robotics.hpp:126-152: bounded trust-region dogleg (CoDo) with
+        the joint ranges [lo, hi] (default: unbounded, +-MAX_SP like joint::range) -> (q, status int8[n], fnorm[n])"""
+        nj = self.njoints
+        big = float(np.finfo(np.float32).max)
+        lo = np.ascontiguousarray(np.full(nj, -big) if lo is None else lo, dtype=np.float64).reshape(nj)
+        hi = np.ascontiguousarray(np.full(nj, big) if hi is None else hi, dtype=np.float64).reshape(nj)
+        pq, n, ld = _in(init, nj, layout, n)
+        pt, nt, ldt = _in(Ttarget, 16, layout, n)
+        if (nt, ldt) != (n, ld):
+            raise ValueError("init and Ttarget must have the same batch shape")
+        qo, pqo = _out(init, nj, layout, n, ld)
+        status = torch.empty(n, dtype=torch.int8, device=init.device)
+        fnorm = torch.empty(n, dtype=torch.float64, device=init.device)
+        with torch.cuda.device(init.device):
+            check(lib.ppx_cuda_batch_ik_codo(self._ps, self._ph, nj, lo.ctypes.data_as(C.c_void_p),
+                                             hi.ctypes.data_as(C.c_void_p), pt, pq, pqo, None,
+                                             C.c_void_p(fnorm.data_ptr()), C.c_void_p(status.data_ptr()), n, layout, ld,
+                                             _stream()))
+        return qo, status, fnorm
+
+    def inverseSpaceNewton(self, Ttarget, init, max_iter=20, layout=AOS, n=None):
+        """the Newton-SVD loop of test/lie_test.cpp:96-113 -> (q, iterations int32[n], status int8[n])"""
         nj = self.njoints
         pq, n, ld = _in(init, nj, layout, n)
         pt, nt, ldt = _in(Ttarget, 16, layout, n)

@@ -337,4 +337,17 @@ int ppx_cuda_host_norm2(int m, int n, const double *A, double *sv, size_t count)
     });
 }
 
+int ppx_cuda_host_ik_codo(const double *screws, const double *home, int njoints, const double *lo, const double *hi,
+                          const double *Ttarget, const double *init, double *q_out, double *x_raw, double *fnorm,
+                          int8_t *status, size_t n)
+{
+    if (njoints != 6)
+        return PPX_ERR_BAD_SHAPE;
+    return pipeline({{Ttarget, 16 * D}, {init, 6 * D}}, {{q_out, 6 * D}, {x_raw, 6 * D}, {fnorm, D}, {status, 1}}, n,
+                    [=](size_t c, void **i, void **o, void *s) {
+                        return ppx_cuda_batch_ik_codo(screws, home, njoints, lo, hi, (cd)i[0], (cd)i[1], (md)o[0], (md)o[1],
+                                                      (md)o[2], (int8_t *)o[3], c, PPX_LAYOUT_AOS, 0, s);
+                    });
+}
+
 } // extern "C"

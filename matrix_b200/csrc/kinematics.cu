@@ -188,6 +188,392 @@ struct OpIkSolve
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// kinematics<6>::inverseSpace(pose, init) of demo/robotics.hpp:126-152 -- the bounded trust-region
+// dogleg details::CoDo<6,6> (include/optimization.hpp:497-829) on f(q) = log(T(q) pose^-1) with the analytic Jacobian
+// [[I,0],[-hat(p),I]] Js(q) of robotics.hpp:134-140 and the joints' ranges as the box.  One instance per thread: the
+// iteration counts are data dependent, so a warp runs as long as its slowest lane (no warp-level collectives inside).
+template <int NJ>
+struct CodoProblem
+{
+    const ChainConst<NJ> &ch;
+    Rigid poseI; // pose^-1
+    __device__ __forceinline__ void f(const double (&q)[NJ], double (&fx)[6]) const
+    {
+        Rigid t, x;
+        poe_fk_jacobian<NJ, true, false>(ch, q, t, [](int, const double(&)[6]) {});
+        rigid_mul(t, poseI, x);
+        SE3_log(x, fx);
+    }
+    // column j of [[I,0],[-hat(p),I]] Js = (w_j ; v_j - p x w_j), p = translation of T(q) pose^-1
+    __device__ __forceinline__ void df(const double (&q)[NJ], double (&jac)[6 * NJ]) const
+    {
+        Rigid t, x;
+        poe_fk_jacobian<NJ, true, true>(ch, q, t, [&](int col, const double(&v)[6]) {
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                jac[6 * col + k] = v[k];
+        });
+        rigid_mul(t, poseI, x);
+#pragma unroll
+        for (int j = 0; j < NJ; j++)
+        {
+            const double w[3] = {jac[6 * j], jac[6 * j + 1], jac[6 * j + 2]};
+            double c[3];
+            cross3(x.p, w, c);
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                jac[6 * j + 3 + k] -= c[k];
+        }
+    }
+};
+
+__device__ __forceinline__ double norm6(const double (&v)[6])
+{
+    double a = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        a = fma(v[i], v[i], a);
+    return sqrt(a);
+}
+__device__ __forceinline__ double dot6(const double (&a)[6], const double (&b)[6])
+{
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        r = fma(a[i], b[i], r);
+    return r;
+}
+__device__ __forceinline__ void matvec6(const double (&A)[36], const double (&x)[6], double (&y)[6])
+{
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+    {
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+            a = fma(A[i + 6 * k], x[k], a);
+        y[i] = a;
+    }
+}
+__device__ __forceinline__ double min6(const double (&v)[6])
+{
+    double m = v[0];
+#pragma unroll
+    for (int i = 1; i < 6; i++)
+        m = fmin(m, v[i]);
+    return m;
+}
+
+// CoDo<6,6>::operator() (optimization.hpp:542-779) with DMatrixCi (:787-808): same constants, same tests, same order
+// of decisions.  Returns CONVERGED / DIVERGED; x is the optimiser's last iterate, y = 0.5 |f|.
+__device__ int codo6(const CodoProblem<6> &pb, const double (&lo)[6], const double (&hi)[6], double (&x)[6], double &y)
+{
+    constexpr double MAX_SP = 3.4028234663852886e+38, sigma = 0.99995, theta = 0.99995, FTOLA = EPS_SP;
+    constexpr unsigned ITMAX = 300;
+    bool legal = true;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        legal = legal && lo[i] <= x[i] && x[i] <= hi[i];
+    if (!legal)
+    {
+        y = MAX_SP;
+        return PPX_STATUS_DIVERGED;
+    }
+    double fx[6], grad[6] = {0, 0, 0, 0, 0, 0}, p[6] = {0, 0, 0, 0, 0, 0};
+    pb.f(x, fx);
+    double fnrm = norm6(fx);
+    unsigned itc = 0;
+    double delta0 = 1.0;
+    int stat = PPX_STATUS_CONVERGED;
+    const double sqrt_eps = sqrt(EPS_DP);
+    while (fnrm > FTOLA && itc++ < ITMAX)
+    {
+        const double fnrm_old = fnrm;
+        double grad_old[6], jac[36], tmp[6], d[6], dsqrt[6], G[6], dgrad[6], pc[6], pn[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            grad_old[i] = grad[i];
+        pb.df(x, jac);
+#pragma unroll
+        for (int i = 0; i < 6; i++) // grad = jac^T fx
+        {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                a = fma(jac[k + 6 * i], fx[k], a);
+            grad[i] = a;
+        }
+        double lambda;
+        if (itc == 1)
+            lambda = fmax(1e-2, norm6(grad));
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                tmp[i] = grad[i] - grad_old[i];
+            lambda = fmax(1e-2, dot6(p, tmp) / dot6(p, p));
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) // Hager scaling, :787-808
+        {
+            if (grad[i] < 0.0 && hi[i] <= MAX_SP)
+                d[i] = 1.0 / (lambda - grad[i] / (hi[i] - x[i]));
+            else if (grad[i] > 0.0 && lo[i] >= -MAX_SP)
+                d[i] = 1.0 / (lambda + grad[i] / (x[i] - lo[i]));
+            else
+                d[i] = 1.0 / lambda;
+        }
+        if (min6(d) < EPS_DP)
+        {
+            stat = PPX_STATUS_DIVERGED;
+            break;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+        {
+            dsqrt[i] = sqrt(d[i]);
+            G[i] = 1.0 / dsqrt[i];
+            dgrad[i] = d[i] * grad[i];
+            tmp[i] = G[i] * dgrad[i];
+        }
+        const double nGdgrad = norm6(tmp);
+        if (norm6(dgrad) < FTOLA)
+            break;
+        double jd[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            tmp[i] = dsqrt[i] * grad[i];
+        matvec6(jac, dgrad, jd);
+        const double ratio = norm6(tmp) / norm6(jd);
+        const double vert = ratio * ratio;
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            pc[i] = -vert * dgrad[i];
+        if (itc == 1)
+        {
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                tmp[i] = grad[i] / G[i];
+            delta0 = norm6(tmp);
+        }
+        // projected Newton step through LU with partial pivoting (linsolve<Factorization::LU>, :608)
+        double lu[36], rx[6];
+#pragma unroll
+        for (int i = 0; i < 36; i++)
+            lu[i] = jac[i];
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            rx[i] = fx[i];
+        bool even;
+        const bool singular = lu_factor_solve<6, 1>(lu, rx, even);
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            pn[i] = singular ? -fx[i] : -rx[i];
+        if (!singular)
+        {
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                pn[i] = fmax(x[i] + pn[i], lo[i]) - x[i];
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                pn[i] = fmin(x[i] + pn[i], hi[i]) - x[i];
+            const double sc = fmax(sigma, 1.0 - norm6(pn));
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                pn[i] *= sc;
+        }
+        // trust-region loop, :620-727
+        double rho = 0.0, delta1 = delta0, xp[6], fxp[6], fxpnrm = 0.0;
+        bool again;
+        do
+        {
+            double pciv[6], alp[6];
+            const bool cauchy = vert * nGdgrad > delta1;
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                pciv[i] = cauchy ? -delta1 / nGdgrad * dgrad[i] : pc[i];
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                alp[i] = fabs(pciv[i]) < EPS_DP ? MAX_SP : fmax((lo[i] - x[i]) / pciv[i], (hi[i] - x[i]) / pciv[i]);
+            double alpha1 = min6(alp);
+            if (alpha1 <= 1.0)
+            {
+                const double sc = fmax(theta, 1.0 - norm6(pciv)) * alpha1;
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+                    pciv[i] *= sc;
+            }
+            if (!singular)
+            {
+                double aa[6], seg[6], bb[6], jp[6];
+                matvec6(jac, pciv, jp);
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+                {
+                    aa[i] = fx[i] + jp[i];
+                    seg[i] = pn[i] - pciv[i];
+                }
+                matvec6(jac, seg, bb);
+                double gamma = 0.0;
+                if (norm6(bb) != 0.0)
+                {
+                    const double gamma_min = -dot6(aa, bb) / dot6(bb, bb);
+                    double Gseg[6], Gpciv[6];
+#pragma unroll
+                    for (int i = 0; i < 6; i++)
+                    {
+                        Gseg[i] = G[i] * seg[i];
+                        Gpciv[i] = G[i] * pciv[i];
+                    }
+                    const double a = dot6(Gseg, Gseg); // SQR(norm2(.))
+                    const double b = dot6(Gpciv, Gseg);
+                    const double c = dot6(Gpciv, Gpciv) - delta1 * delta1;
+                    const double root = sqrt(b * b - a * c);
+                    const double l1 = (-b + (-b >= 0.0 ? fabs(root) : -fabs(root))) / a;
+                    const double l2 = c / (l1 * a);
+                    if (gamma_min > 0.0)
+                    {
+                        gamma = fmin(gamma_min, fmax(l1, l2));
+                        if (gamma > 1.0)
+                        {
+#pragma unroll
+                            for (int i = 0; i < 6; i++)
+                                alp[i] = seg[i] != 0.0 ? fmax((lo[i] - x[i] - pciv[i]) / seg[i], (hi[i] - x[i] - pciv[i]) / seg[i])
+                                                       : MAX_SP;
+                            gamma = fmin(theta * min6(alp), gamma);
+                        }
+                    }
+                    else
+                    {
+                        gamma = fmax(gamma_min, fmin(l1, l2));
+                        if (gamma < 0.0)
+                        {
+#pragma unroll
+                            for (int i = 0; i < 6; i++)
+                                alp[i] = seg[i] != 0.0 ? fmax((x[i] + pciv[i] - lo[i]) / seg[i], (x[i] + pciv[i] - hi[i]) / seg[i])
+                                                       : MAX_SP;
+                            gamma = fmax(-theta * min6(alp), gamma);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+                    p[i] = (1.0 - gamma) * pciv[i] + gamma * pn[i];
+            }
+            else
+            {
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+                    p[i] = pciv[i];
+            }
+            double jp2[6], lin[6], Gp[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                xp[i] = x[i] + p[i];
+            pb.f(xp, fxp);
+            fxpnrm = norm6(fxp);
+            matvec6(jac, p, jp2);
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+            {
+                lin[i] = fx[i] + jp2[i];
+                Gp[i] = G[i] * p[i];
+            }
+            rho = (fnrm - fxpnrm) / (fnrm - norm6(lin));
+            again = false;
+            if (rho < 0.25)
+            {
+                delta1 = fmin(0.25 * delta0, 0.5 * norm6(Gp));
+                again = delta1 > sqrt_eps;
+            }
+            else if (rho > 0.75)
+                delta0 = fmax(delta1, 2.0 * norm6(Gp)); // :735-738 (only reached when the loop ends here)
+        } while (again);
+        if (rho < 0.25 && delta1 < sqrt_eps)
+        {
+            stat = PPX_STATUS_DIVERGED;
+            break;
+        }
+        bool need_update = false;
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+        {
+            x[i] = xp[i];
+            if (x[i] < lo[i] + 1e3 * EPS_DP)
+            {
+                x[i] = lo[i] + 1e3 * EPS_DP;
+                need_update = true;
+            }
+            if (x[i] > hi[i] - 1e3 * EPS_DP)
+            {
+                x[i] = hi[i] - 1e3 * EPS_DP;
+                need_update = true;
+            }
+        }
+        if (need_update)
+        {
+            pb.f(x, fx);
+            fnrm = norm6(fx);
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                fx[i] = fxp[i];
+            fnrm = fxpnrm;
+        }
+        if (fabs(fnrm - fnrm_old) < FTOLA * fnrm && fnrm > FTOLA)
+            break;
+    }
+    y = 0.5 * fnrm;
+    return stat;
+}
+
+struct OpIkCodo
+{
+    static constexpr int BLOCK = 128, MINB = 1, MAXW = 16;
+    ChainConst<6> ch;
+    double lo[6], hi[6];
+    const double *Tt;
+    const double *init;
+    double *q_out;
+    double *x_raw;
+    double *fnorm;
+    int8_t *status;
+    template <class IO>
+    __device__ __forceinline__ void operator()(const IO &io) const
+    {
+        double q0[6], m[16], x[6], y;
+        io.load(init, q0);
+        io.load(Tt, m);
+        Rigid pose;
+        rigid_from_record(m, pose);
+        if (!io.valid) // keep dead lanes out of the iteration: identity target, zero start converge immediately
+            rigid_identity(pose);
+        CodoProblem<6> pb{ch, Rigid()};
+        rigid_inv(pose, pb.poseI);
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            x[i] = q0[i];
+        const int st = io.valid ? codo6(pb, lo, hi, x, y) : PPX_STATUS_DIVERGED;
+        double out[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            out[i] = st == PPX_STATUS_CONVERGED ? x[i] : q0[i]; // inverseSpace, robotics.hpp:151
+        io.store(q_out, out);
+        if (x_raw != nullptr)
+            io.store(x_raw, x);
+        if (io.valid)
+        {
+            if (fnorm != nullptr)
+                fnorm[io.i] = y;
+            if (status != nullptr)
+                status[io.i] = (int8_t)st;
+        }
+    }
+};
+
 template <int NJ>
 int fk_jacobian_n(const double *screws, const double *home, const double *q, double *T, double *Js, size_t n,
                   int layout, size_t ld, void *stream)
@@ -280,6 +666,26 @@ int ppx_cuda_batch_ik_solve(const double *screws, const double *home, int njoint
         return PPX_OK;
     PPX_CHECK_PTRS(screws, home, q0, Ttarget, q_out);
     return ik_solve_n<6>(screws, home, q0, Ttarget, max_iter, q_out, iters, status, n, layout, ld, stream);
+}
+
+int ppx_cuda_batch_ik_codo(const double *screws, const double *home, int njoints, const double *lo, const double *hi,
+                           const double *Ttarget, const double *init, double *q_out, double *x_raw, double *fnorm,
+                           int8_t *status, size_t n, int layout, size_t ld, void *stream)
+{
+    if (njoints != 6) // CoDo<N,6> solves a square system through linsolve<LU> (optimization.hpp:608)
+        return PPX_ERR_BAD_SHAPE;
+    if (n == 0)
+        return PPX_OK;
+    PPX_CHECK_PTRS(screws, home, lo, hi, Ttarget, init, q_out);
+    OpIkCodo op;
+    fold_chain<6>(screws, home, op.ch);
+    for (int i = 0; i < 6; i++)
+    {
+        op.lo[i] = lo[i];
+        op.hi[i] = hi[i];
+    }
+    op.Tt = Ttarget, op.init = init, op.q_out = q_out, op.x_raw = x_raw, op.fnorm = fnorm, op.status = status;
+    return dispatch(layout, op, n, ld, stream);
 }
 
 } // extern "C"

@@ -125,7 +125,22 @@ class Kinematics:
                                                _p(Vs), n))
         return (qo, Vs) if want_Vs else qo
 
-    def inverseSpace(self, Ttarget, init, max_iter=20):
+    def inverseSpace(self, Ttarget, init, lo=None, hi=None):
+        """demo/robotics.hpp:126-152 (CoDo trust region) -> (q, status, fnorm)"""
+        nj = self.njoints
+        big = float(np.finfo(np.float32).max)
+        lo = np.ascontiguousarray(np.full(nj, -big) if lo is None else lo, dtype=np.float64).reshape(nj)
+        hi = np.ascontiguousarray(np.full(nj, big) if hi is None else hi, dtype=np.float64).reshape(nj)
+        q, Tt = _arr(init, nj), _arr(Ttarget, 16)
+        n = q.shape[0]
+        qo = np.empty((n, nj))
+        status = np.empty(n, dtype=np.int8)
+        fnorm = np.empty(n)
+        check(lib.ppx_cuda_host_ik_codo(_p(self.screws), _p(self.home), nj, _p(lo), _p(hi), _p(Tt), _p(q), _p(qo), None,
+                                        _p(fnorm), _p(status), n))
+        return qo, status, fnorm
+
+    def inverseSpaceNewton(self, Ttarget, init, max_iter=20):
         q, Tt = _arr(init, self.njoints), _arr(Ttarget, 16)
         n = q.shape[0]
         qo = np.empty((n, self.njoints))

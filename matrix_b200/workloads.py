@@ -202,4 +202,23 @@ class IkNewtonStep(Workload):
 
 
 
-WORKLOADS = {w.name: w for w in (Ur5FkJacobian, Ur5FkJacobianAoS, Se3ExpLog, LinsolveQR43, Svd66, EigSym4, IkNewtonStep)}
+class IkCodo(Workload):
+    """SURVEY 8(f) row 4: kinematics<6>::inverseSpace, the trust-region IK the reference's demo and benchmark time
+    (demo/main.cpp:371-377, benchmark/benchmark.cpp:167-189): start 0.05 rad off the solution on every joint"""
+    name = "inverse_space_codo"
+    n_default = 1 << 22
+    bytes_in, bytes_out = 48 + 128, 48 + 8 + 1
+    bound = "fp64 / latency (data-dependent iteration counts)"
+
+    def setup(self):
+        self.kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
+        q = _device_records(self.n, 6, synth.SEEDS["ik_newton_step"], self.first, -np.pi, np.pi, self.device) * 0.95
+        self.Tt = self.kin.forwardSpace(q.contiguous())
+        self.q0 = (q - 0.05).contiguous()
+        self.lo, self.hi = -np.pi * np.ones(6), np.pi * np.ones(6)
+
+    def step(self):
+        self.out = self.kin.inverseSpace(self.Tt, self.q0, self.lo, self.hi)
+
+
+WORKLOADS = {w.name: w for w in (Ur5FkJacobian, Ur5FkJacobianAoS, Se3ExpLog, LinsolveQR43, Svd66, EigSym4, IkNewtonStep, IkCodo)}

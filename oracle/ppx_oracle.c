@@ -1109,3 +1109,291 @@ int ppxo_ik_solve(const double *screws, const double *home, int nj, const double
          }
          memcpy(q_out + nj * i, q, sizeof(double) * nj); if (iters) iters[i] = iter;)
 }
+
+/* ------------------------------------------------------------ bounded trust-region IK (CoDo) */
+
+#define MAX_SP ((double)FLT_MAX) /* include/exprtmpl.hpp:14 */
+static double sqr(double a) { return a * a; }
+
+/* the residual and Jacobian kinematics<N>::inverseSpace hands to CoDo, demo/robotics.hpp:128-140 */
+static void codo_f(const double *screws, const double *home, int nj, const double *poseI, const double *q, double *fx)
+{
+    double Tsb[16], X[16];
+    fk1(screws, home, nj, q, Tsb);
+    gemm(4, 4, 4, Tsb, poseI, X);
+    SE3_log1(X, fx);
+}
+static void codo_df(const double *screws, const double *home, int nj, const double *poseI, const double *q,
+                    double *jac)
+{
+    double Tsb[16], X[16], p[3], hp[9], JpI[36], Js[6 * MAXD];
+    fk1(screws, home, nj, q, Tsb);
+    gemm(4, 4, 4, Tsb, poseI, X);
+    pos_of(X, p);
+    hat3(p, hp);
+    eye(6, JpI);
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++)
+            JpI[(r + 3) + 6 * c] = -1 * hp[r + 3 * c];
+    jac1(screws, nj, q, Js);
+    gemm(6, 6, nj, JpI, Js, jac);
+}
+
+static double dot_n(const double *a, const double *b, int n)
+{
+    double acc = 0.0;
+    for (int i = 0; i < n; i++)
+        acc = acc + a[i] * b[i];
+    return acc;
+}
+static double vmin(const double *a, int n)
+{
+    double m = a[0];
+    for (int i = 1; i < n; i++)
+        if (a[i] < m)
+            m = a[i];
+    return m;
+}
+
+/* details::CoDo<6,6>::operator(), include/optimization.hpp:542-779, with DMatrixCi (:787-808).
+ * Returns the status (1 CONVERGED / 2 DIVERGED); x is updated in place, *y = 0.5 |f|. */
+static int codo6(const double *screws, const double *home, const double *poseI, const double *lo, const double *hi,
+                 double *x, double *y)
+{
+    enum { N = 6 };
+    const double sigma = 0.99995, theta = 0.99995, FTOLA = EPS_SP;
+    const unsigned ITMAX = 300;
+    for (int i = 0; i < N; i++)
+        if (!(lo[i] <= x[i] && x[i] <= hi[i]))
+        {
+            *y = MAX_SP;
+            return 2;
+        }
+    double fx[N], grad[N] = {0}, p[N] = {0};
+    codo_f(screws, home, N, poseI, x, fx);
+    double fnrm = vnorm(fx, N);
+    unsigned itc = 0;
+    double delta0 = 1.0;
+    int stat = 1;
+    while (fnrm > FTOLA && itc++ < ITMAX)
+    {
+        double fnrm_old = fnrm, grad_old[N], jac[36], jacT[36], tmp[N], d[N], dsqrt[N], G[N], dgrad[N], pc[N], pn[N];
+        memcpy(grad_old, grad, sizeof(grad));
+        codo_df(screws, home, N, poseI, x, jac);
+        transpose(6, 6, jac, jacT);
+        gemm(6, 6, 1, jacT, fx, grad);
+        double lambda;
+        if (itc == 1)
+            lambda = fmax(1e-2, vnorm(grad, N));
+        else
+        {
+            for (int i = 0; i < N; i++)
+                tmp[i] = grad[i] - grad_old[i];
+            lambda = fmax(1e-2, dot_n(p, tmp, N) / dot_n(p, p, N));
+        }
+        for (int i = 0; i < N; i++) /* Hager scaling */
+        {
+            if (grad[i] < 0.0 && hi[i] <= MAX_SP)
+                d[i] = 1.0 / (lambda - grad[i] / (hi[i] - x[i]));
+            else if (grad[i] > 0 && lo[i] >= -MAX_SP)
+                d[i] = 1.0 / (lambda + grad[i] / (x[i] - lo[i]));
+            else
+                d[i] = 1.0 / lambda;
+        }
+        if (vmin(d, N) < EPS_DP)
+        {
+            stat = 2;
+            break;
+        }
+        for (int i = 0; i < N; i++)
+        {
+            dsqrt[i] = sqrt(d[i]);
+            G[i] = 1.0 / dsqrt[i];
+            dgrad[i] = d[i] * grad[i];
+        }
+        for (int i = 0; i < N; i++)
+            tmp[i] = G[i] * dgrad[i];
+        double nGdgrad = vnorm(tmp, N);
+        if (vnorm(dgrad, N) < FTOLA)
+            break;
+        double jd[N];
+        for (int i = 0; i < N; i++)
+            tmp[i] = dsqrt[i] * grad[i];
+        gemm(6, 6, 1, jac, dgrad, jd);
+        double vert = sqr(vnorm(tmp, N) / vnorm(jd, N));
+        for (int i = 0; i < N; i++)
+            pc[i] = -vert * dgrad[i];
+        if (itc == 1)
+        {
+            for (int i = 0; i < N; i++)
+                tmp[i] = grad[i] / G[i];
+            delta0 = vnorm(tmp, N);
+        }
+        lu_t f;
+        double rx[N];
+        lu_factor(N, jac, &f);
+        memcpy(rx, fx, sizeof(rx));
+        if (!f.singular)
+            lu_solve_vec(N, &f, rx);
+        for (int i = 0; i < N; i++)
+            pn[i] = -1 * rx[i];
+        if (!f.singular)
+        {
+            for (int i = 0; i < N; i++)
+                pn[i] = fmax(x[i] + pn[i], lo[i]) - x[i];
+            for (int i = 0; i < N; i++)
+                pn[i] = fmin(x[i] + pn[i], hi[i]) - x[i];
+            double sc = fmax(sigma, 1 - vnorm(pn, N));
+            for (int i = 0; i < N; i++)
+                pn[i] = sc * pn[i];
+        }
+        double rho = 0.0, delta1 = delta0, xp[N], fxp[N], fxpnrm;
+        int again;
+        do
+        {
+            double pciv[N], alp[N];
+            memcpy(pciv, pc, sizeof(pciv));
+            if (vert * nGdgrad > delta1)
+                for (int i = 0; i < N; i++)
+                    pciv[i] = -delta1 / nGdgrad * dgrad[i];
+            for (int i = 0; i < N; i++)
+                alp[i] = fabs(pciv[i]) < EPS_DP ? MAX_SP : fmax((lo[i] - x[i]) / pciv[i], (hi[i] - x[i]) / pciv[i]);
+            double alpha1 = vmin(alp, N);
+            if (alpha1 <= 1)
+            {
+                double sc = fmax(theta, 1 - vnorm(pciv, N)) * alpha1;
+                for (int i = 0; i < N; i++)
+                    pciv[i] *= sc;
+            }
+            if (!f.singular)
+            {
+                double aa[N], seg[N], bb[N], jp[N];
+                gemm(6, 6, 1, jac, pciv, jp);
+                for (int i = 0; i < N; i++)
+                {
+                    aa[i] = fx[i] + jp[i];
+                    seg[i] = pn[i] - pciv[i];
+                }
+                gemm(6, 6, 1, jac, seg, bb);
+                double gamma = 0.0;
+                if (vnorm(bb, N) != 0)
+                {
+                    double gamma_min = -dot_n(aa, bb, N) / dot_n(bb, bb, N);
+                    double Gseg[N], Gpciv[N];
+                    for (int i = 0; i < N; i++)
+                    {
+                        Gseg[i] = G[i] * seg[i];
+                        Gpciv[i] = G[i] * pciv[i];
+                    }
+                    double a = sqr(vnorm(Gseg, N));
+                    double b = dot_n(Gpciv, Gseg, N);
+                    double c = sqr(vnorm(Gpciv, N)) - sqr(delta1);
+                    double l1 = (-b + sign2(sqrt(b * b - a * c), -b)) / a;
+                    double l2 = c / (l1 * a);
+                    if (gamma_min > 0)
+                    {
+                        double gamma_end = fmax(l1, l2);
+                        gamma = fmin(gamma_min, gamma_end);
+                        if (gamma > 1)
+                        {
+                            for (int i = 0; i < N; i++)
+                                alp[i] = seg[i] != 0 ? fmax((lo[i] - x[i] - pciv[i]) / seg[i], (hi[i] - x[i] - pciv[i]) / seg[i])
+                                                     : MAX_SP;
+                            alpha1 = vmin(alp, N);
+                            gamma = fmin(theta * alpha1, gamma);
+                        }
+                    }
+                    else
+                    {
+                        double gamma_end = fmin(l1, l2);
+                        gamma = fmax(gamma_min, gamma_end);
+                        if (gamma < 0)
+                        {
+                            for (int i = 0; i < N; i++)
+                                alp[i] = seg[i] != 0 ? fmax((x[i] + pciv[i] - lo[i]) / seg[i], (x[i] + pciv[i] - hi[i]) / seg[i])
+                                                     : MAX_SP;
+                            alpha1 = vmin(alp, N);
+                            gamma = fmax(-theta * alpha1, gamma);
+                        }
+                    }
+                }
+                for (int i = 0; i < N; i++)
+                    p[i] = (1 - gamma) * pciv[i] + gamma * pn[i];
+            }
+            else
+                memcpy(p, pciv, sizeof(pciv));
+            double jp2[N], lin[N];
+            for (int i = 0; i < N; i++)
+                xp[i] = x[i] + p[i];
+            codo_f(screws, home, N, poseI, xp, fxp);
+            fxpnrm = vnorm(fxp, N);
+            gemm(6, 6, 1, jac, p, jp2);
+            for (int i = 0; i < N; i++)
+                lin[i] = fx[i] + jp2[i];
+            rho = (fnrm - fxpnrm) / (fnrm - vnorm(lin, N));
+            again = 0;
+            if (rho < 0.25)
+            {
+                double Gp[N];
+                for (int i = 0; i < N; i++)
+                    Gp[i] = G[i] * p[i];
+                delta1 = fmin(0.25 * delta0, 0.5 * vnorm(Gp, N));
+                again = delta1 > sqrt(EPS_DP);
+            }
+        } while (again);
+        if (rho < 0.25 && delta1 < sqrt(EPS_DP))
+        {
+            stat = 2;
+            break;
+        }
+        if (rho > 0.75)
+        {
+            double Gp[N];
+            for (int i = 0; i < N; i++)
+                Gp[i] = G[i] * p[i];
+            delta0 = fmax(delta1, 2 * vnorm(Gp, N));
+        }
+        memcpy(x, xp, sizeof(xp));
+        int need_update = 0;
+        for (int i = 0; i < N; i++)
+        {
+            if (x[i] < lo[i] + 1e3 * EPS_DP)
+            {
+                x[i] = lo[i] + 1e3 * EPS_DP;
+                need_update = 1;
+            }
+            if (x[i] > hi[i] - 1e3 * EPS_DP)
+            {
+                x[i] = hi[i] - 1e3 * EPS_DP;
+                need_update = 1;
+            }
+        }
+        if (need_update)
+        {
+            codo_f(screws, home, N, poseI, x, fx);
+            fnrm = vnorm(fx, N);
+        }
+        else
+        {
+            memcpy(fx, fxp, sizeof(fxp));
+            fnrm = fxpnrm;
+        }
+        if (fabs(fnrm - fnrm_old) < FTOLA * fnrm && fnrm > FTOLA)
+            break;
+    }
+    *y = 0.5 * fnrm;
+    return stat;
+}
+
+int ppxo_ik_codo(const double *screws, const double *home, int nj, const double *lo, const double *hi,
+                 const double *Tt, const double *init, double *q_out, double *x_raw, double *fnorm,
+                 signed char *status, size_t count, int nthreads)
+{
+    if (nj != 6)
+        return -1;
+    LOOP(double poseI[16]; double x[6]; double y; SE3_inv1(Tt + 16 * i, poseI); memcpy(x, init + 6 * i, sizeof(x));
+         int st = codo6(screws, home, poseI, lo, hi, x, &y);
+         /* inverseSpace: result.s == CONVERGED ? result.x : init (demo/robotics.hpp:151) */
+         memcpy(q_out + 6 * i, st == 1 ? x : init + 6 * i, sizeof(x));
+         if (x_raw) memcpy(x_raw + 6 * i, x, sizeof(x)); if (fnorm) fnorm[i] = y; if (status) status[i] = (signed char)st;)
+}

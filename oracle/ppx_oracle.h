@@ -95,6 +95,14 @@ int ppxo_ik_solve(const double *screws, const double *home, int njoints,
                   const double *q0, const double *Ttarget, int max_iter,
                   double *q_out, int *iters, size_t count, int nthreads);
 
+/* kinematics<N>::inverseSpace(pose, init) of demo/robotics.hpp:126-152: bounded trust-region dogleg (details::CoDo<N,6>,
+ * include/optimization.hpp:497-829) on f(q) = log(T(q) pose^-1) with the analytic Jacobian of :134-140 and the joint
+ * ranges lo/hi (njoints each).  q_out = result.x if CONVERGED else init (as inverseSpace returns it); x_raw (the
+ * optimiser's last iterate), fnorm (OptResult::y = 0.5 |f|) and status (CONVERGED / DIVERGED) may be NULL. */
+int ppxo_ik_codo(const double *screws, const double *home, int njoints, const double *lo, const double *hi,
+                 const double *Ttarget, const double *init, double *q_out, double *x_raw, double *fnorm,
+                 signed char *status, size_t count, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

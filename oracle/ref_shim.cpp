@@ -137,6 +137,54 @@ namespace
         return 0;
     }
 
+    template <size_t N>
+    int ik_codo(const double *screws, const double *home, const double *lo, const double *hi, const double *Tt,
+                const double *init, double *q_out, double *x_raw, double *fnorm, signed char *status, size_t count,
+                int nthreads)
+    {
+        kinematics<N> chain = make_chain<N>(screws, home);
+        for (size_t i = 0; i < N; i++)
+        {
+            chain.JointList()[i].range = {lo[i], hi[i]};
+        }
+#pragma omp parallel for schedule(static) num_threads(threads_or_all(nthreads))
+        for (long long i = 0; i < (long long)count; i++)
+        {
+            kinematics<N> kin = chain;
+            const auto q0 = load<N, 1>(init + N * i);
+            const SE3 pose(load<4, 4>(Tt + 16 * i));
+            store(q_out + N * i, kin.inverseSpace(pose, q0)); // demo/robotics.hpp:126-152
+            if (x_raw || fnorm || status)
+            {
+                // the same optimiser call as inverseSpace makes (:128-150), to expose OptResult's y and s as well
+                auto fx = [&kin, &pose](const MatrixS<N, 1> &q)
+                { return (kin.forwardSpace(q) * pose.I()).log(); };
+                auto dfx = [&kin, &pose](const MatrixS<N, 1> &q, const se3 &)
+                {
+                    auto Tsb = kin.forwardSpace(q) * pose.I();
+                    auto JpI = eye<6>();
+                    JpI.template sub<3, 3, false>(3, 0) = -1 * hat(Tsb.Pos());
+                    return JpI * kin.jacobiSpace(q);
+                };
+                details::CoDo<N, 6> codo(fx, dfx, load<N, 1>(lo), load<N, 1>(hi));
+                auto r = codo(q0);
+                if (x_raw)
+                {
+                    store(x_raw + N * i, r.x);
+                }
+                if (fnorm)
+                {
+                    fnorm[i] = r.y;
+                }
+                if (status)
+                {
+                    status[i] = (signed char)r.s;
+                }
+            }
+        }
+        return 0;
+    }
+
     template <size_t M, size_t N>
     int qr_solve(const double *A, const double *b, double *x, signed char *status, size_t count, int nthreads)
     {
@@ -350,6 +398,17 @@ extern "C"
         case 6: return ik_loop<6>(screws, home, q0, Ttarget, max_iter, q_out, iters, count, nthreads);
         default: return -1;
         }
+    }
+
+    int ppxo_ik_codo(const double *screws, const double *home, int njoints, const double *lo, const double *hi,
+                     const double *Ttarget, const double *init, double *q_out, double *x_raw, double *fnorm,
+                     signed char *status, size_t count, int nthreads)
+    {
+        if (njoints != 6)
+        {
+            return -1; // CoDo<N,6> solves a square system through linsolve<LU> (optimization.hpp:608)
+        }
+        return ik_codo<6>(screws, home, lo, hi, Ttarget, init, q_out, x_raw, fnorm, status, count, nthreads);
     }
 
 #define SHAPE2(fn, M_, N_, ...) \

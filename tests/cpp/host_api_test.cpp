@@ -75,8 +75,15 @@ int main()
         auto r2 = UR5.jacobiSpace(q);
         EXPECT(r2 == result2);
         SE3 TargetPose{0.0, 1.0, 0.0, 0.0, -1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.095, 0.109, 0.988, 1.0};
-        auto j = UR5.inverseSpace(TargetPose, {0.0, -1.5, 0.0, 0.0, 1.5, 0.0});
+        auto j = UR5.inverseSpaceNewton(TargetPose, {0.0, -1.5, 0.0, 0.0, 1.5, 0.0});
         EXPECT(UR5.forwardSpace(j) == TargetPose);
+        // demo/main.cpp:369-375: CoDo trust-region inverseSpace with (-pi, pi) joint ranges
+        for (auto &jt : UR5.JointList())
+            jt.range = {-PI, PI};
+        kinematics<6>::Q qd{0.336058, 1.69911, -0.445658, -1.25227, 0.00013744, -2.71554};
+        SE3 Td = UR5.forwardSpace(qd);
+        auto qs = UR5.inverseSpace(Td, qd - 0.05);
+        EXPECT(norm2(qs - qd) < 1e-5);
     }
     // test/matrix_test.cpp:819-850 with the documented spellings of README.md:70-95
     {

@@ -163,6 +163,15 @@ def main():
     fx["ik.q_out"], fx["ik.Vs"] = ref.ik_newton_step(S, M, qi, Tt)
     fx["ik.q_solved"], fx["ik.iters"] = ref.ik_solve(S, M, qi, Tt, 20)
 
+    # kinematics<6>::inverseSpace (CoDo trust region, demo/robotics.hpp:126-152) with the demo's (-pi, pi) joint ranges
+    qc = synth.joint_angles(N, seed=synth.SEEDS["ik_newton_step"]) * 0.95
+    Tc = ref.poe_fk_jacobian(S, M, qc + synth.ik_offsets(N), want_Js=False)[0]
+    qc = np.vstack([qc, np.array([[4.0, 0, 0, 0, 0, 0]])])  # last row: illegal start, outside the box
+    Tc = np.vstack([Tc, Tc[:1]])
+    lo, hi = -np.pi * np.ones(6), np.pi * np.ones(6)
+    fx["codo.init"], fx["codo.Ttarget"], fx["codo.lo"], fx["codo.hi"] = qc, Tc, lo, hi
+    fx["codo.q_out"], fx["codo.x_raw"], fx["codo.fnorm"], fx["codo.status"] = ref.ik_codo(S, M, lo, hi, Tc, qc)
+
     out = os.path.join(HERE, "ref_outputs.npz")
     np.savez_compressed(out, **fx)
     print(f"wrote {out}: {len(fx)} arrays, {os.path.getsize(out) / 1024:.0f} KiB")

@@ -146,6 +146,23 @@ class Oracle:
                    it.ctypes.data_as(_ip), C.c_size_t(n), C.c_int(self.nthreads))
         return qo, it
 
+    def ik_codo(self, screws, home, lo, hi, Tt, init):
+        """kinematics<6>::inverseSpace (CoDo) -> (q_out, x_raw, fnorm, status)"""
+        screws = np.ascontiguousarray(screws, dtype=np.float64).reshape(-1, 6)
+        nj = screws.shape[0]
+        home = np.ascontiguousarray(home, dtype=np.float64).reshape(16)
+        lo = np.ascontiguousarray(lo, dtype=np.float64).reshape(nj)
+        hi = np.ascontiguousarray(hi, dtype=np.float64).reshape(nj)
+        init = _in(init, nj)
+        Tt = _in(Tt, 16)
+        n = init.shape[0]
+        qo, xr = np.empty((n, nj)), np.empty((n, nj))
+        fn = np.empty(n)
+        st = np.empty(n, dtype=np.int8)
+        self._call("ppxo_ik_codo", _d(screws), _d(home), C.c_int(nj), _d(lo), _d(hi), _d(Tt), _d(init), _d(qo), _d(xr),
+                   _d(fn), st.ctypes.data_as(_bp), C.c_size_t(n), C.c_int(self.nthreads))
+        return qo, xr, fn, st
+
     # -- dense solvers --------------------------------------------------------------------
     def linsolve_qr(self, m, n, A, b):
         A = _in(A, m * n)

@@ -50,7 +50,7 @@ def run(mb, fn, layout, *arrays, **kw):
     def back(t):
         if t is None:
             return None
-        if t.dtype != torch.float64:
+        if t.dtype != torch.float64 or t.dim() == 1:  # dense per-instance vectors (status, iterations, fnorm)
             return t.cpu().numpy()
         return (t if layout == "aos" else mb.to_aos(t, n)).cpu().numpy()
 
@@ -198,7 +198,7 @@ def test_golden_ur5(mb, golden):
     # test/lie_test.cpp:211-216: Newton-SVD IK from (0,-1.5,0,0,1.5,0) reaches the target pose
     q0 = dev(np.array(g["ik_start"]).reshape(1, 6))
     Tt = dev(np.array(g["ik_target"]).reshape(1, 16))
-    qs, it, st = kin.inverseSpace(Tt, q0, g["ik_max_iter"])
+    qs, it, st = kin.inverseSpaceNewton(Tt, q0, g["ik_max_iter"])
     Tq = kin.forwardSpace(qs).cpu().numpy()
     assert np.abs(Tq[0] - np.array(g["ik_target"])).max() < g["tol"]
     assert int(st[0]) == mb.CONVERGED and 1 <= int(it[0]) <= 20
@@ -234,7 +234,7 @@ def test_ik_solve_loop(mb, port):
     n = 1 << 13
     kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
     q, Tt, kappa = _ik_inputs(port, n, first=5000)
-    qs, it, st = kin.inverseSpace(dev(Tt), dev(q), 20)
+    qs, it, st = kin.inverseSpaceNewton(dev(Tt), dev(q), 20)
     qs, it, st = qs.cpu().numpy(), it.cpu().numpy(), st.cpu().numpy()
     rq, rit = port.ik_solve(synth.UR5_SCREWS, synth.UR5_HOME, q, Tt, 20)
     conv = st == mb.CONVERGED
@@ -632,3 +632,47 @@ def test_svd_eig_scale_with_their_input(mb, port, scale):
         assert np.all(np.abs(np.sort(w2, axis=1) - np.sort(rw, axis=1)).max(axis=1) / rw.max(axis=1) < REL)
         rd, _ = port.eig_sym(4, S * scale, True)
         assert np.all(np.abs(d2 - rd).max(axis=1) / np.abs(rd).max(axis=1) < REL)
+
+
+# --------------------------------------------------------------------------------------- SURVEY 8(f) row 4
+def test_inverse_space_codo(mb, port):
+    """kinematics<6>::inverseSpace (bounded trust-region dogleg, demo/robotics.hpp:126-152) vs the oracle."""
+    n = 1 << 13
+    S, M = synth.UR5_SCREWS, synth.UR5_HOME
+    q = synth.joint_angles(n, seed=synth.SEEDS["ik_newton_step"]) * 0.95  # inside the (-pi, pi) joint ranges
+    Tt = port.poe_fk_jacobian(S, M, q + synth.ik_offsets(n), want_Js=False)[0]
+    lo, hi = -np.pi * np.ones(6), np.pi * np.ones(6)  # demo/main.cpp:363-368
+    kin = mb.Kinematics(S, M)
+    for layout in LAYOUTS:
+        qs, st, fn = run(mb, lambda t_, q_, layout: kin.inverseSpace(t_, q_, lo, hi, layout=layout), layout, Tt, q)
+        rq, rx, rfn, rst = port.ik_codo(S, M, lo, hi, Tt, q)
+        assert (st == rst).mean() > 0.999
+        conv = (st == mb.CONVERGED) & (rst == mb.CONVERGED)
+        assert conv.mean() > 0.99
+        # CoDo reports CONVERGED unless the trust region collapses -- also when it stops on "no improvement" or on a
+        # box-constrained minimum (optimization.hpp:590-593, 772-775) -- so "solved" is |f| <= FTOLA = EPS_SP (:501, 567)
+        solved, rsolved = fn <= 0.5 * 1.1920928955078125e-07, rfn <= 0.5 * 1.1920928955078125e-07
+        assert solved[conv].mean() > 0.99 and abs(solved.mean() - rsolved.mean()) < 5e-3
+        assert (solved == rsolved).mean() > 0.995
+        conv &= solved & rsolved
+        # solved instances reproduce the target pose to that accuracy, like the reference's result does
+        Tq = port.poe_fk_jacobian(S, M, qs, want_Js=False)[0]
+        assert np.abs(Tq[conv] - Tt[conv]).max() < 5e-7
+        # the trajectories are rounding-sensitive (trust-region decisions); the converged joint vectors still agree to
+        # the optimiser's tolerance times the conditioning of the solution
+        Jf = port.poe_fk_jacobian(S, M, rq, want_T=False)[1]
+        sv = np.linalg.svd(Jf.reshape(n, 6, 6), compute_uv=False)
+        kf = sv[:, 0] / sv[:, -1]
+        ok = conv & (kf < 1e2)
+        assert ok.mean() > 0.5
+        assert np.all(np.abs(qs[ok] - rq[ok]).max(axis=1) < 1e-6 * kf[ok])
+    # illegal start (outside the box) -> DIVERGED and init returned (optimization.hpp:552-556, robotics.hpp:151)
+    bad = q[:4].copy()
+    bad[:, 0] = 4.0
+    qs, st, fn = run(mb, lambda t_, q_, layout: kin.inverseSpace(t_, q_, lo, hi, layout=layout), "aos", Tt[:4], bad)
+    assert np.all(st == mb.DIVERGED) and np.array_equal(qs, bad)
+    # demo/main.cpp:369-375: the demo's own configuration, start 0.05 rad away on every joint
+    qd = np.array([[0.336058, 1.69911, -0.445658, -1.25227, 0.00013744, -2.71554]])
+    Td = port.poe_fk_jacobian(S, M, qd, want_Js=False)[0]
+    qs, st, fn = run(mb, lambda t_, q_, layout: kin.inverseSpace(t_, q_, lo, hi, layout=layout), "aos", Td, qd - 0.05)
+    assert st[0] == mb.CONVERGED and np.abs(qs - qd).max() < 1e-5

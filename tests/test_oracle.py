@@ -170,6 +170,8 @@ def _replay(o, fx):
     out["sym6.d_sorted"], out["sym6.z_sorted"] = o.eig_sym(6, fx["sym6.S"], True)
     out["ik.q_out"], out["ik.Vs"] = o.ik_newton_step(S, M, fx["ik.q"], fx["ik.Ttarget"])
     out["ik.q_solved"], out["ik.iters"] = o.ik_solve(S, M, fx["ik.q"], fx["ik.Ttarget"], 20)
+    out["codo.q_out"], out["codo.x_raw"], out["codo.fnorm"], out["codo.status"] = o.ik_codo(
+        S, M, fx["codo.lo"], fx["codo.hi"], fx["codo.Ttarget"], fx["codo.init"])
     return out
 
 
@@ -206,6 +208,9 @@ def test_fixture_edge_cases_hit_every_branch(fixtures):
     assert np.array_equal(fixtures["lstsq.x_qr"][sing], fixtures["lstsq.b"][sing][:, :3])
     assert set(np.unique(fixtures["dense6.status_lu"])) == {0, 3}
     assert fixtures["ik.iters"].max() <= 20 and fixtures["ik.iters"].min() >= 1
+    # CoDo: converged instances and the illegal start that is rejected and handed back (optimization.hpp:552-556)
+    st = fixtures["codo.status"]
+    assert st[-1] == 2 and np.array_equal(fixtures["codo.q_out"][-1], fixtures["codo.init"][-1]) and (st[:-1] == 1).mean() > 0.9
 
 
 # ----------------------------------------------------------------------------- 3. live, larger batches
@@ -231,6 +236,9 @@ def test_port_matches_reference_live(port, ref_strict):
     qi = synth.joint_angles(n, first=1000, seed=synth.SEEDS["ik_newton_step"])
     Tt = ref_strict.poe_fk_jacobian(S, M, qi + synth.ik_offsets(n, first=1000), want_Js=False)[0]
     for x, y in zip(port.ik_newton_step(S, M, qi, Tt), ref_strict.ik_newton_step(S, M, qi, Tt)):
+        assert bits_equal(x, y)
+    lo, hi = -np.pi * np.ones(6), np.pi * np.ones(6)
+    for x, y in zip(port.ik_codo(S, M, lo, hi, Tt, qi * 0.95), ref_strict.ik_codo(S, M, lo, hi, Tt, qi * 0.95)):
         assert bits_equal(x, y)
 
 
