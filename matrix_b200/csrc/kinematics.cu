@@ -198,7 +198,9 @@ struct CodoProblem
 {
     const ChainConst<NJ> &ch;
     Rigid poseI; // pose^-1
-    __device__ __forceinline__ void f(const double (&q)[NJ], double (&fx)[6]) const
+    // f and df are deliberately NOT inlined: the optimiser calls f from three places, and one copy of the kinematics
+    // keeps the iteration body inside the instruction cache (ncu: `no_instruction` was the top stall when inlined)
+    __device__ __noinline__ void f(const double (&q)[NJ], double (&fx)[6]) const
     {
         Rigid t, x;
         poe_fk_jacobian<NJ, true, false>(ch, q, t, [](int, const double(&)[6]) {});
@@ -206,7 +208,7 @@ struct CodoProblem
         SE3_log(x, fx);
     }
     // column j of [[I,0],[-hat(p),I]] Js = (w_j ; v_j - p x w_j), p = translation of T(q) pose^-1
-    __device__ __forceinline__ void df(const double (&q)[NJ], double (&jac)[6 * NJ]) const
+    __device__ __noinline__ void df(const double (&q)[NJ], double (&jac)[6 * NJ]) const
     {
         Rigid t, x;
         poe_fk_jacobian<NJ, true, true>(ch, q, t, [&](int col, const double(&v)[6]) {
@@ -266,28 +268,65 @@ __device__ __forceinline__ double min6(const double (&v)[6])
 }
 
 // CoDo<6,6>::operator() (optimization.hpp:542-779) with DMatrixCi (:787-808): same constants, same tests, same order
-// of decisions.  Returns CONVERGED / DIVERGED; x is the optimiser's last iterate, y = 0.5 |f|.
-__device__ int codo6(const CodoProblem<6> &pb, const double (&lo)[6], const double (&hi)[6], double (&x)[6], double &y)
+// of decisions -- written as a state machine (codo_init + one codo_step per trip of the optimiser's while loop) so that
+// a lane whose instance has finished can pick up the next instance instead of idling until the slowest lane of its
+// warp is done (trip counts range from 3 to ITMAX = 300; ncu on the plain per-thread loop: 5.4 of 32 lanes active).
+struct CodoState
 {
-    constexpr double MAX_SP = 3.4028234663852886e+38, sigma = 0.99995, theta = 0.99995, FTOLA = EPS_SP;
-    constexpr unsigned ITMAX = 300;
+    double x[6], fx[6], grad[6], p[6];
+    double fnrm, delta0, y;
+    unsigned itc;
+    int stat;
+};
+
+constexpr double CODO_MAX_SP = 3.4028234663852886e+38; // MAX_SP, include/exprtmpl.hpp:14
+
+// -> true when the instance is already finished (illegal start, :546-556)
+__device__ __forceinline__ bool codo_init(const CodoProblem<6> &pb, const double (&lo)[6], const double (&hi)[6],
+                                          CodoState &st)
+{
     bool legal = true;
 #pragma unroll
     for (int i = 0; i < 6; i++)
-        legal = legal && lo[i] <= x[i] && x[i] <= hi[i];
+    {
+        legal = legal && lo[i] <= st.x[i] && st.x[i] <= hi[i];
+        st.grad[i] = 0.0;
+        st.p[i] = 0.0;
+    }
+    st.itc = 0;
+    st.delta0 = 1.0;
+    st.stat = PPX_STATUS_CONVERGED;
     if (!legal)
     {
-        y = MAX_SP;
-        return PPX_STATUS_DIVERGED;
+        st.y = CODO_MAX_SP;
+        st.stat = PPX_STATUS_DIVERGED;
+        return true;
     }
-    double fx[6], grad[6] = {0, 0, 0, 0, 0, 0}, p[6] = {0, 0, 0, 0, 0, 0};
-    pb.f(x, fx);
-    double fnrm = norm6(fx);
-    unsigned itc = 0;
-    double delta0 = 1.0;
-    int stat = PPX_STATUS_CONVERGED;
+    pb.f(st.x, st.fx);
+    st.fnrm = norm6(st.fx);
+    st.y = 0.5 * st.fnrm;
+    return false;
+}
+
+// one trip of `while (fnrm > FTOLA && itc++ < ITMAX)` (:567-776) -> true when the optimiser is done
+__device__ __forceinline__ bool codo_step(const CodoProblem<6> &pb, const double (&lo)[6], const double (&hi)[6],
+                                          CodoState &st)
+{
+    constexpr double MAX_SP = CODO_MAX_SP, sigma = 0.99995, theta = 0.99995, FTOLA = EPS_SP;
+    constexpr unsigned ITMAX = 300;
+    double(&x)[6] = st.x;
+    double(&fx)[6] = st.fx;
+    double(&grad)[6] = st.grad;
+    double(&p)[6] = st.p;
+    double &fnrm = st.fnrm;
+    double &delta0 = st.delta0;
     const double sqrt_eps = sqrt(EPS_DP);
-    while (fnrm > FTOLA && itc++ < ITMAX)
+    if (!(fnrm > FTOLA && st.itc++ < ITMAX))
+    {
+        st.y = 0.5 * fnrm;
+        return true;
+    }
+    const unsigned itc = st.itc;
     {
         const double fnrm_old = fnrm;
         double grad_old[6], jac[36], tmp[6], d[6], dsqrt[6], G[6], dgrad[6], pc[6], pn[6];
@@ -326,8 +365,9 @@ __device__ int codo6(const CodoProblem<6> &pb, const double (&lo)[6], const doub
         }
         if (min6(d) < EPS_DP)
         {
-            stat = PPX_STATUS_DIVERGED;
-            break;
+            st.stat = PPX_STATUS_DIVERGED;
+            st.y = 0.5 * fnrm;
+            return true;
         }
 #pragma unroll
         for (int i = 0; i < 6; i++)
@@ -339,7 +379,10 @@ __device__ int codo6(const CodoProblem<6> &pb, const double (&lo)[6], const doub
         }
         const double nGdgrad = norm6(tmp);
         if (norm6(dgrad) < FTOLA)
-            break;
+        {
+            st.y = 0.5 * fnrm;
+            return true;
+        }
         double jd[6];
 #pragma unroll
         for (int i = 0; i < 6; i++)
@@ -492,8 +535,9 @@ __device__ int codo6(const CodoProblem<6> &pb, const double (&lo)[6], const doub
         } while (again);
         if (rho < 0.25 && delta1 < sqrt_eps)
         {
-            stat = PPX_STATUS_DIVERGED;
-            break;
+            st.stat = PPX_STATUS_DIVERGED;
+            st.y = 0.5 * fnrm;
+            return true;
         }
         bool need_update = false;
 #pragma unroll
@@ -523,16 +567,18 @@ __device__ int codo6(const CodoProblem<6> &pb, const double (&lo)[6], const doub
                 fx[i] = fxp[i];
             fnrm = fxpnrm;
         }
+        st.y = 0.5 * fnrm;
         if (fabs(fnrm - fnrm_old) < FTOLA * fnrm && fnrm > FTOLA)
-            break;
+            return true;
     }
-    y = 0.5 * fnrm;
-    return stat;
+    return false;
 }
 
-struct OpIkCodo
+// Persistent warps with per-lane work refill: every lane owns one instance at a time and, when its optimiser
+// finishes, claims the next unprocessed instance from a global counter (one atomicAdd per warp per refill round).
+// All lanes of a warp then execute the same codo_step in lockstep, each on its own instance.
+struct IkCodoArgs
 {
-    static constexpr int BLOCK = 128, MINB = 1, MAXW = 16;
     ChainConst<6> ch;
     double lo[6], hi[6];
     const double *Tt;
@@ -541,39 +587,96 @@ struct OpIkCodo
     double *x_raw;
     double *fnorm;
     int8_t *status;
-    template <class IO>
-    __device__ __forceinline__ void operator()(const IO &io) const
-    {
-        double q0[6], m[16], x[6], y;
-        io.load(init, q0);
-        io.load(Tt, m);
-        Rigid pose;
-        rigid_from_record(m, pose);
-        if (!io.valid) // keep dead lanes out of the iteration: identity target, zero start converge immediately
-            rigid_identity(pose);
-        CodoProblem<6> pb{ch, Rigid()};
-        rigid_inv(pose, pb.poseI);
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-            x[i] = q0[i];
-        const int st = io.valid ? codo6(pb, lo, hi, x, y) : PPX_STATUS_DIVERGED;
-        double out[6];
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-            out[i] = st == PPX_STATUS_CONVERGED ? x[i] : q0[i]; // inverseSpace, robotics.hpp:151
-        io.store(q_out, out);
-        if (x_raw != nullptr)
-            io.store(x_raw, x);
-        if (io.valid)
-        {
-            if (fnorm != nullptr)
-                fnorm[io.i] = y;
-            if (status != nullptr)
-                status[io.i] = (int8_t)st;
-        }
-    }
 };
 
+template <int LAYOUT>
+__device__ __forceinline__ double rec_get(const double *base, size_t i, int k, int width, size_t ld)
+{
+    return LAYOUT == LAYOUT_AOS ? __ldcs(base + i * width + k) : __ldcs(base + (size_t)k * ld + i);
+}
+template <int LAYOUT>
+__device__ __forceinline__ void rec_put(double *base, size_t i, int k, int width, size_t ld, double v)
+{
+    if (LAYOUT == LAYOUT_AOS)
+        __stcs(base + i * width + k, v);
+    else
+        __stcs(base + (size_t)k * ld + i, v);
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(128, 2) ik_codo_kernel(const __grid_constant__ IkCodoArgs a, size_t n, size_t ld,
+                                                        unsigned long long *next)
+{
+    const unsigned lane = threadIdx.x & 31;
+    CodoProblem<6> pb{a.ch, Rigid()};
+    CodoState st;
+    double q0[6];
+    size_t idx = 0;
+    bool busy = false, fresh = false;
+    for (;;)
+    {
+        // refill: lanes without work claim consecutive instances
+        const unsigned want = __ballot_sync(0xffffffffu, !busy);
+        if (want)
+        {
+            unsigned long long first = 0;
+            if (lane == (unsigned)(__ffs(want) - 1))
+                first = atomicAdd(next, (unsigned long long)__popc(want));
+            first = __shfl_sync(0xffffffffu, first, __ffs(want) - 1);
+            if (!busy)
+            {
+                idx = (size_t)first + __popc(want & ((1u << lane) - 1));
+                if (idx < n)
+                {
+                    double m[16];
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                        m[k] = rec_get<LAYOUT>(a.Tt, idx, k, 16, ld);
+#pragma unroll
+                    for (int k = 0; k < 6; k++)
+                    {
+                        q0[k] = rec_get<LAYOUT>(a.init, idx, k, 6, ld);
+                        st.x[k] = q0[k];
+                    }
+                    Rigid pose;
+                    rigid_from_record(m, pose);
+                    rigid_inv(pose, pb.poseI);
+                    busy = true;
+                    fresh = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, busy))
+            break;
+        if (busy)
+        {
+            bool done = false;
+            if (fresh)
+            {
+                done = codo_init(pb, a.lo, a.hi, st);
+                fresh = false;
+            }
+            if (!done)
+                done = codo_step(pb, a.lo, a.hi, st);
+            if (done)
+            {
+#pragma unroll
+                for (int k = 0; k < 6; k++)
+                {
+                    // inverseSpace returns the optimiser's x only if CONVERGED, else init (robotics.hpp:151)
+                    rec_put<LAYOUT>(a.q_out, idx, k, 6, ld, st.stat == PPX_STATUS_CONVERGED ? st.x[k] : q0[k]);
+                    if (a.x_raw != nullptr)
+                        rec_put<LAYOUT>(a.x_raw, idx, k, 6, ld, st.x[k]);
+                }
+                if (a.fnorm != nullptr)
+                    a.fnorm[idx] = st.y;
+                if (a.status != nullptr)
+                    a.status[idx] = (int8_t)st.stat;
+                busy = false;
+            }
+        }
+    }
+}
 template <int NJ>
 int fk_jacobian_n(const double *screws, const double *home, const double *q, double *T, double *Js, size_t n,
                   int layout, size_t ld, void *stream)
@@ -677,15 +780,40 @@ int ppx_cuda_batch_ik_codo(const double *screws, const double *home, int njoints
     if (n == 0)
         return PPX_OK;
     PPX_CHECK_PTRS(screws, home, lo, hi, Ttarget, init, q_out);
-    OpIkCodo op;
-    fold_chain<6>(screws, home, op.ch);
+    if (layout != PPX_LAYOUT_AOS && layout != PPX_LAYOUT_SOA)
+        return PPX_ERR_BAD_LAYOUT;
+    if (layout == PPX_LAYOUT_SOA && ld < n)
+        return PPX_ERR_BAD_ARGUMENT;
+    IkCodoArgs a;
+    fold_chain<6>(screws, home, a.ch);
     for (int i = 0; i < 6; i++)
     {
-        op.lo[i] = lo[i];
-        op.hi[i] = hi[i];
+        a.lo[i] = lo[i];
+        a.hi[i] = hi[i];
     }
-    op.Tt = Ttarget, op.init = init, op.q_out = q_out, op.x_raw = x_raw, op.fnorm = fnorm, op.status = status;
-    return dispatch(layout, op, n, ld, stream);
+    a.Tt = Ttarget, a.init = init, a.q_out = q_out, a.x_raw = x_raw, a.fnorm = fnorm, a.status = status;
+    DeviceInfo info;
+    int device = 0;
+    int rc = device_info(info, device);
+    if (rc != PPX_OK)
+        return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    // the work counter lives for this launch only (stream-ordered allocation, zeroed on the stream)
+    unsigned long long *next = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&next, sizeof(*next), s);
+    if (e != cudaSuccess)
+        return (int)e;
+    cudaMemsetAsync(next, 0, sizeof(*next), s);
+    auto kern = layout == PPX_LAYOUT_AOS ? ik_codo_kernel<LAYOUT_AOS> : ik_codo_kernel<LAYOUT_SOA>;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);
+    const size_t want = (n + 127) / 128;
+    const size_t cap = (size_t)info.sms * (per_sm > 0 ? per_sm : 1);
+    kern<<<(unsigned)(want < cap ? want : cap), 128, 0, s>>>(a, n, ld, next);
+    g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);
+    e = cudaPeekAtLastError();
+    cudaFreeAsync(next, s);
+    return (int)e;
 }
 
 } // extern "C"

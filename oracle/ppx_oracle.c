@@ -1116,8 +1116,10 @@ int ppxo_ik_solve(const double *screws, const double *home, int nj, const double
 static double sqr(double a) { return a * a; }
 
 /* the residual and Jacobian kinematics<N>::inverseSpace hands to CoDo, demo/robotics.hpp:128-140 */
+static _Thread_local long g_codo_fevals; /* diagnostic: residual evaluations of the current codo6 call */
 static void codo_f(const double *screws, const double *home, int nj, const double *poseI, const double *q, double *fx)
 {
+    g_codo_fevals++;
     double Tsb[16], X[16];
     fk1(screws, home, nj, q, Tsb);
     gemm(4, 4, 4, Tsb, poseI, X);
@@ -1396,4 +1398,12 @@ int ppxo_ik_codo(const double *screws, const double *home, int nj, const double 
          /* inverseSpace: result.s == CONVERGED ? result.x : init (demo/robotics.hpp:151) */
          memcpy(q_out + 6 * i, st == 1 ? x : init + 6 * i, sizeof(x));
          if (x_raw) memcpy(x_raw + 6 * i, x, sizeof(x)); if (fnorm) fnorm[i] = y; if (status) status[i] = (signed char)st;)
+}
+
+/* port-only diagnostic (not part of ppx_oracle.h): residual evaluations per instance of ppxo_ik_codo */
+int ppxo_ik_codo_fevals(const double *screws, const double *home, const double *lo, const double *hi, const double *Tt,
+                        const double *init, long *fevals, size_t count, int nthreads)
+{
+    LOOP(double poseI[16]; double x[6]; double y; SE3_inv1(Tt + 16 * i, poseI); memcpy(x, init + 6 * i, sizeof(x));
+         g_codo_fevals = 0; codo6(screws, home, poseI, lo, hi, x, &y); fevals[i] = g_codo_fevals;)
 }
