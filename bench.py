@@ -164,6 +164,8 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--all-ops", action="store_true",
+                    help="time every batched entry point (kernel only, SoA) next to its CPU reference; one JSON line")
     args = ap.parse_args()
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -214,6 +216,43 @@ def main():
         return max_over_ranks(ev[0].elapsed_time(ev[steps])), per
 
     hbm_peak, peak_src = measured_peaks()
+    if args.all_ops:
+        # one line per C-ABI entry point that is not already a BASELINE workload: kernel-only inst/s and GB/s on
+        # device-resident SoA data, with the CPU reference (all host threads, 2^20-instance sample) beside it
+        import time as _t
+        from matrix_b200 import ops_table
+        from bench_cpu import NTHREADS, cpu_op, load_cpu_oracle
+        oracle, kind = load_cpu_oracle()
+        rows = []
+        for op in ops_table.make_ops():
+            op.setup(device)
+            for _ in range(3):
+                op.step()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            torch.cuda.synchronize()
+            ev[0].record()
+            for i in range(5):
+                op.step()
+                ev[i + 1].record()
+            torch.cuda.synchronize()
+            ms = statistics.mean(ev[i].elapsed_time(ev[i + 1]) for i in range(5))
+            sample = 1 << 20 if "ik_" not in op.name else 1 << 18
+            fn = cpu_op(op.name, oracle, sample)
+            fn()
+            t0 = _t.perf_counter()
+            fn()
+            cpu_s = _t.perf_counter() - t0
+            gbs = op.n * op.bytes / (ms * 1e-3) / 1e9
+            rows.append({"op": op.name, "reference": op.ref, "instances": op.n, "kernel_ms": ms,
+                         "value": op.n / (ms * 1e-3), "unit": "instances/s", "algorithmic_bytes_per_instance": op.bytes,
+                         "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "touched_bytes_per_instance": op.touched,
+                         "hbm_frac_touched": gbs / hbm_peak * op.touched / op.bytes,
+                         "cpu_value": sample / cpu_s, "cpu_cores": NTHREADS,
+                         "cpu_kind": kind})
+            op.step = None
+            torch.cuda.empty_cache()
+        print(json.dumps({"all_ops": rows, "hbm_peak_gbs": hbm_peak, "layout": "soa (device resident)", "dtype": "f64"}))
+        return
     cls = WORKLOADS[args.workload]
     n = args.n or cls.n_default
     w = cls(n, device, first=rank * n)

@@ -118,6 +118,86 @@ def cpu_inverse_space_codo(oracle, n, first=0):
                                                None, None, C.c_size_t(n), C.c_int(NTHREADS)))
 
 
+def _lie_inputs(oracle, n):
+    xi = synth.se3_twists(n)
+    T = oracle.se3_exp(xi)
+    T2 = oracle.se3_exp(xi[::-1].copy())
+    w = np.ascontiguousarray(xi[:, :3])
+    R = oracle.so3_exp(w)
+    return xi, T, T2, w, R
+
+
+def _unary(oracle, fn, x, wout):
+    out = np.empty((x.shape[0], wout))
+    _touch(out)
+    f = getattr(oracle.lib, fn)
+    return lambda: _ok(f(_d(x), _d(out), C.c_size_t(x.shape[0]), C.c_int(NTHREADS)))
+
+
+def cpu_op(name, oracle, n):
+    """CPU closure for an entry of matrix_b200/ops_table.py (same distribution, n instances)"""
+    S = np.ascontiguousarray(synth.UR5_SCREWS)
+    M = np.ascontiguousarray(synth.UR5_HOME)
+    if name in ("so3_exp", "SO3_log", "se3_exp", "SE3_log", "SE3_inv", "SE3_Adt", "se3_adt", "SE3_mul", "so3_ljacinv"):
+        xi, T, T2, w, R = _lie_inputs(oracle, n)
+        if name == "so3_exp":
+            return _unary(oracle, "ppxo_so3_exp", w, 9)
+        if name == "SO3_log":
+            return _unary(oracle, "ppxo_SO3_log", R, 3)
+        if name == "se3_exp":
+            return _unary(oracle, "ppxo_se3_exp", xi, 16)
+        if name == "SE3_log":
+            return _unary(oracle, "ppxo_SE3_log", T, 6)
+        if name == "SE3_inv":
+            return _unary(oracle, "ppxo_SE3_inv", T, 16)
+        if name == "SE3_Adt":
+            return _unary(oracle, "ppxo_SE3_Adt", T, 36)
+        if name == "se3_adt":
+            return _unary(oracle, "ppxo_se3_adt", xi, 36)
+        if name == "SE3_mul":
+            out = np.empty_like(T)
+            _touch(out)
+            return lambda: _ok(oracle.lib.ppxo_SE3_mul(_d(T), _d(T2), _d(out), C.c_size_t(n), C.c_int(NTHREADS)))
+        out = np.empty((n, 9))
+        _touch(out)
+        return lambda: _ok(oracle.lib.ppxo_so3_jac(C.c_int(1), _d(w), _d(out), C.c_size_t(n), C.c_int(NTHREADS)))
+    if name == "ik_solve_newton_loop":
+        q = synth.joint_angles(n, seed=synth.SEEDS["ik_newton_step"])
+        Tt = oracle.poe_fk_jacobian(S, M, q + synth.ik_offsets(n), want_Js=False)[0]
+        qo = np.empty((n, 6))
+        it = np.empty(n, dtype=np.int32)
+        _touch(qo)
+        return lambda: _ok(oracle.lib.ppxo_ik_solve(_d(S), _d(M), C.c_int(6), _d(q), _d(Tt), C.c_int(20), _d(qo),
+                                                    it.ctypes.data_as(C.POINTER(C.c_int)), C.c_size_t(n), C.c_int(NTHREADS)))
+    m, nn = {"linsolve_svd_6x6": (6, 6), "linsolve_lu_6x6": (6, 6), "inverse_6x6": (6, 6), "det_6x6": (6, 6),
+             "pinv_4x3": (4, 3), "norm2_6x6": (6, 6), "svd_4x3": (4, 3)}[name]
+    A = synth.dense(n, m, nn, seed=0x301)
+    b = synth.dense(n, m, 1, seed=0x302)
+    st = np.empty(n, dtype=np.int8)
+    bp = st.ctypes.data_as(C.POINTER(C.c_byte))
+    if name == "linsolve_svd_6x6":
+        x = np.empty((n, 6)); _touch(x)
+        return lambda: _ok(oracle.lib.ppxo_linsolve_svd(C.c_int(6), C.c_int(6), _d(A), _d(b), _d(x), C.c_size_t(n), C.c_int(NTHREADS)))
+    if name == "linsolve_lu_6x6":
+        x = np.empty((n, 6)); _touch(x)
+        return lambda: _ok(oracle.lib.ppxo_linsolve_lu(C.c_int(6), _d(A), _d(b), _d(x), bp, C.c_size_t(n), C.c_int(NTHREADS)))
+    if name == "inverse_6x6":
+        x = np.empty((n, 36)); _touch(x)
+        return lambda: _ok(oracle.lib.ppxo_inverse(C.c_int(6), _d(A), _d(x), C.c_size_t(n), C.c_int(NTHREADS)))
+    if name == "det_6x6":
+        x = np.empty(n); _touch(x)
+        return lambda: _ok(oracle.lib.ppxo_det(C.c_int(6), _d(A), _d(x), C.c_size_t(n), C.c_int(NTHREADS)))
+    if name == "pinv_4x3":
+        x = np.empty((n, 12)); _touch(x)
+        return lambda: _ok(oracle.lib.ppxo_pinv(C.c_int(4), C.c_int(3), _d(A), _d(x), C.c_size_t(n), C.c_int(NTHREADS)))
+    if name == "norm2_6x6":
+        x = np.empty(n); _touch(x)
+        return lambda: _ok(oracle.lib.ppxo_norm2(C.c_int(6), C.c_int(6), _d(A), _d(x), C.c_size_t(n), C.c_int(NTHREADS)))
+    U, w, V = np.empty((n, 12)), np.empty((n, 3)), np.empty((n, 9))
+    _touch(U, w, V)
+    return lambda: _ok(oracle.lib.ppxo_svd(C.c_int(4), C.c_int(3), _d(A), _d(U), _d(w), _d(V), C.c_size_t(n), C.c_int(NTHREADS)))
+
+
 CPU = {
     "ur5_fk_jacobian": cpu_ur5_fk_jacobian,
     "ur5_fk_jacobian_aos": cpu_ur5_fk_jacobian,
