@@ -512,6 +512,26 @@ PPX_DEV int linsolve_qr(double (&A)[M * N], double (&b)[M], double (&x)[N])
     return singular ? 3 : 0;
 }
 
+// Branch-free reciprocal square root / reciprocal: the hardware seed (MUFU.RSQ64H / MUFU.RCP64H, relative
+// error ~2^-22) refined by one third-order step, full fp64 accuracy for normal, non-zero arguments.  Unlike
+// sqrt() and operator/ there is no special-case slow path, hence no call and no convergence barrier in the
+// instruction stream: the independent rotation chains of a Jacobi round stay in one basic block and overlap.
+// (x = 0 gives inf/NaN; callers discard that lane's result with a select.)
+PPX_DEV double rsqrt_nr(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0); // 1 - x y^2
+    return fma(y * e, fma(0.375, e, 0.5), y); // y (1 + e/2 + 3 e^2/8)
+}
+PPX_DEV double rcp_nr(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0); // 1 - x y
+    return fma(y, fma(e, e, e), y);   // y (1 + e + e^2)
+}
+
 // LU<n> with partial pivoting, include/linalg.hpp:448-533, in registers.  The pivot row is data dependent, so the
 // row exchange is a predicated swap against every candidate row (compile-time indices only).  Pivot choice follows
 // the reference: first row of maximal |A(row,k)|, SINGULAR as soon as that maximum is below EPS_DP (:473-477).
@@ -523,6 +543,7 @@ PPX_DEV bool lu_factor_solve(double (&A)[N * N], double (&B)[N * (NRHS > 0 ? NRH
 {
     bool singular = false;
     even = true;
+    double ipiv[N];
 #pragma unroll
     for (int k = 0; k < N; k++)
     {
@@ -557,11 +578,13 @@ PPX_DEV bool lu_factor_solve(double (&A)[N * N], double (&B)[N * (NRHS > 0 ? NRH
                 B[r + c * N] = sw ? x : y;
             }
         }
-        const double ipiv = 1.0 / A[k + k * N];
+        // one branch-free reciprocal per pivot serves the elimination and, later, the back substitution of every
+        // right-hand side (the reference divides each time; the difference is one rounding)
+        ipiv[k] = rcp_nr(A[k + k * N]);
 #pragma unroll
         for (int r = k + 1; r < N; r++)
         {
-            const double wgt = A[r + k * N] * ipiv;
+            const double wgt = A[r + k * N] * ipiv[k];
             A[r + k * N] = wgt;
 #pragma unroll
             for (int c = k + 1; c < N; c++)
@@ -582,7 +605,7 @@ PPX_DEV bool lu_factor_solve(double (&A)[N * N], double (&B)[N * (NRHS > 0 ? NRH
 #pragma unroll
             for (int j = r + 1; j < N; j++)
                 sum = fma(-A[r + j * N], B[j + c * N], sum);
-            B[r + c * N] = sum / A[r + r * N];
+            B[r + c * N] = sum * ipiv[r];
         }
     }
     return singular;
@@ -628,26 +651,6 @@ PPX_DEV void pow2_rescale(double (&a)[L], int shift) // one warp-uniform branch 
         for (int i = 0; i < L; i++)
             a[i] = pow2_mul(a[i], shift);
     }
-}
-
-// Branch-free reciprocal square root / reciprocal: the hardware seed (MUFU.RSQ64H / MUFU.RCP64H, relative
-// error ~2^-22) refined by one third-order step, full fp64 accuracy for normal, non-zero arguments.  Unlike
-// sqrt() and operator/ there is no special-case slow path, hence no call and no convergence barrier in the
-// instruction stream: the independent rotation chains of a Jacobi round stay in one basic block and overlap.
-// (x = 0 gives inf/NaN; callers discard that lane's result with a select.)
-PPX_DEV double rsqrt_nr(double x)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-(x * y), y, 1.0); // 1 - x y^2
-    return fma(y * e, fma(0.375, e, 0.5), y); // y (1 + e/2 + 3 e^2/8)
-}
-PPX_DEV double rcp_nr(double x)
-{
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-x, y, 1.0); // 1 - x y
-    return fma(y, fma(e, e, e), y);   // y (1 + e + e^2)
 }
 
 // Jacobi rotation that annihilates the off-diagonal g of [[a, g], [g, b]]: with d = b - a, h = sqrt(d^2 + 4 g^2),
