@@ -676,3 +676,72 @@ def test_inverse_space_codo(mb, port):
     Td = port.poe_fk_jacobian(S, M, qd, want_Js=False)[0]
     qs, st, fn = run(mb, lambda t_, q_, layout: kin.inverseSpace(t_, q_, lo, hi, layout=layout), "aos", Td, qd - 0.05)
     assert st[0] == mb.CONVERGED and np.abs(qs - qd).max() < 1e-5
+
+
+# --------------------------------------------------------------------------------------- full BASELINE sizes, configs 3-5
+def _soa_workload(name, n=None):
+    from matrix_b200.workloads import WORKLOADS
+    cls = WORKLOADS[name]
+    w = cls(n or cls.n_default, torch.device("cuda", 0))
+    w.setup()
+    w.step()
+    torch.cuda.synchronize()
+    return w
+
+
+def test_full_size_64M_linsolve_qr(mb):
+    """BASELINE config 3 at full size (2^26 systems): least-squares optimality A^T (A x - b) = 0 and status, in chunks."""
+    w = _soa_workload("linsolve_qr_4x3")
+    assert int((w.status != 0).sum()) == 0  # U(-1,1) 4x3 matrices: no squared column norm below eps
+    worst = 0.0
+    step = 1 << 23
+    for lo in range(0, w.n, step):
+        A = w.A[:, lo:lo + step].view(3, 4, -1)  # [col, row, i]
+        x = w.x[:, lo:lo + step]
+        r = torch.einsum("cri,ci->ri", A, x) - w.b[:, lo:lo + step]
+        g = torch.einsum("cri,ri->ci", A, r)
+        # |A^T r| relative to |A|^2 |x| + |A| |b| (backward-stable least squares)
+        scale = (A * A).sum(dim=(0, 1)) * x.abs().max(dim=0).values + 2.0
+        worst = max(worst, float((g.abs().max(dim=0).values / scale).max()))
+    assert worst < 1e-13
+
+
+def test_full_size_16M_svd_and_eig(mb):
+    """BASELINE config 4 at full size: U diag(w) V^T = A, V^T V = I (SVD 6x6); S z = z d, sorted d (eig 4x4)."""
+    w = _soa_workload("svd_6x6")
+    step = 1 << 21
+    for lo in range(0, w.n, step):
+        A = w.A[:, lo:lo + step].view(6, 6, -1)  # [col, row, i]
+        U = w.U[:, lo:lo + step].view(6, 6, -1)
+        V = w.V[:, lo:lo + step].view(6, 6, -1)
+        s = w.w[:, lo:lo + step]
+        rec = torch.einsum("jri,ji,jci->cri", U, s, V)  # sum_j U[:,j] s_j V[c,j]
+        assert float((rec - A).abs().max()) < 1e-13
+        G = torch.einsum("ari,bri->abi", V, V)
+        assert float((G - torch.eye(6, dtype=torch.float64, device="cuda")[:, :, None]).abs().max()) < 1e-13
+        assert bool((s >= 0).all())
+    del w
+    torch.cuda.empty_cache()
+    e = _soa_workload("eig_sym_4")
+    S = e.S.view(4, 4, -1)
+    Z = e.z.view(4, 4, -1)  # [col, row, i]
+    res = torch.einsum("kri,jki->jri", S, Z) - Z * e.d[:, None, :]
+    assert float(res.abs().max()) < 1e-13
+    assert bool((e.d[1:] >= e.d[:-1]).all())
+
+
+def test_full_size_32M_ik_newton_step(mb):
+    """BASELINE config 5 at its per-GPU size (2^25 = 256M / 8): one Newton step reduces the pose error
+    |log(T(q)^-1 Ttarget)| quadratically wherever the Jacobian is well conditioned."""
+    w = _soa_workload("ik_newton_step")
+
+    def pose_err(q):
+        T = w.kin.forwardSpace(q, layout=mb.SOA)
+        X = mb.SE3_mul(mb.SE3_inv(T, layout=mb.SOA), w.Tt, layout=mb.SOA)
+        return mb.SE3_log(X, layout=mb.SOA).norm(dim=0)
+
+    e0, e1 = pose_err(w.q), pose_err(w.qo)
+    assert bool(torch.isfinite(w.qo).all())
+    good = e1 < 10 * e0 * e0 + 1e-12  # quadratic contraction
+    assert float(good.double().mean()) > 0.97  # the rest sits near UR5 singularities (SURVEY 8d)
+    assert float(e1.median()) < 0.05 * float(e0.median())
