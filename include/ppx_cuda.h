@@ -79,6 +79,10 @@ int ppx_cuda_fill_uniform(double *out, size_t count, uint64_t seed, uint64_t fir
  * in *tflops; synchronises the stream (measurement helper, not part of the hot path). */
 int ppx_cuda_fp64_peak_probe(double *tflops, void *stream);
 
+/* measurement helper: writes `planes` SoA component planes of n doubles (mode 0: 64-bit stores, one instance per
+ * thread, the pattern of the batch kernels; mode 1: 128-bit stores, two instances per thread) */
+int ppx_cuda_probe_write(double *out, int planes, size_t n, size_t ld, int mode, void *stream);
+
 /* ---- Lie group / algebra ------------------------------------------------------------------- */
 /* so3::exp, include/liegroup.hpp:116-133.  w: 3 -> R: 9 */
 int ppx_cuda_batch_so3_exp(const double *w, double *R, size_t n, int layout, size_t ld, void *stream);

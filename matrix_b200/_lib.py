@@ -41,6 +41,7 @@ _SIGNATURES = {
     "ppx_cuda_soa_to_aos": [_vp, _vp, _i, _sz, _sz, _vp],
     "ppx_cuda_fill_uniform": [_vp, _sz, _u64, _u64, _d, _d, _vp],
     "ppx_cuda_fp64_peak_probe": [C.POINTER(_d), _vp],
+    "ppx_cuda_probe_write": [_vp, _i, _sz, _sz, _i, _vp],
     "ppx_cuda_batch_so3_exp": [_vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_batch_SO3_log": [_vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_batch_se3_exp": [_vp, _vp, _sz, _i, _sz, _vp],

@@ -19,6 +19,24 @@
 namespace ppx_dev
 {
 
+// store / load flavour, selectable at build time for experiments (-DPPX_STORE=0 plain, 1 .cs evict-first [default],
+// 2 .wt write-through; -DPPX_LOAD likewise)
+#ifndef PPX_STORE
+#define PPX_STORE 1
+#endif
+__device__ __forceinline__ void stg(double *p, double v)
+{
+#if PPX_STORE == 0
+    *p = v;
+#elif PPX_STORE == 2
+    __stwt(p, v);
+#elif PPX_STORE == 3
+    __stcg(p, v);
+#else
+    __stcs(p, v);
+#endif
+}
+
 constexpr int LAYOUT_AOS = 0;
 constexpr int LAYOUT_SOA = 1;
 
@@ -62,7 +80,7 @@ struct TileIO<LAYOUT_SOA>
         {
 #pragma unroll
             for (int k = 0; k < D; k++)
-                __stcs(base + (size_t)k * ld + i, r[k]);
+                stg(base + (size_t)k * ld + i, r[k]);
         }
     }
 
@@ -74,7 +92,7 @@ struct TileIO<LAYOUT_SOA>
         {
 #pragma unroll
             for (int k = 0; k < CNT; k++)
-                __stcs(base + (size_t)(off + k) * ld + i, r[k]);
+                stg(base + (size_t)(off + k) * ld + i, r[k]);
         }
     }
 
@@ -184,7 +202,7 @@ struct TileIO<LAYOUT_AOS>
             if (j < total)
             {
                 const int rec = j / D;
-                __stcs(dst + j, ws[rec * DP + (j - rec * D)]);
+                stg(dst + j, ws[rec * DP + (j - rec * D)]);
             }
         }
         __syncwarp();

@@ -61,6 +61,27 @@ __global__ void __launch_bounds__(256) k_fp64_probe(double *sink, int iters)
         sink[0] = s;
 }
 
+// measurement helper: the store side of the SoA kernels in isolation -- `planes` component planes of n doubles,
+// thread i writing element i of every plane (mode 0: one 64-bit store per plane, like the batch kernels; mode 1: two
+// instances per thread, one 128-bit store per plane)
+template <int MODE>
+__global__ void k_probe_write(double *__restrict__ out, int planes, size_t n, size_t ld)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    if (MODE == 0)
+    {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+            for (int k = 0; k < planes; k++)
+                __stcs(out + (size_t)k * ld + i, (double)k);
+    }
+    else
+    {
+        for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i + 1 < n; i += 2 * stride)
+            for (int k = 0; k < planes; k++)
+                __stcs(reinterpret_cast<double2 *>(out + (size_t)k * ld + i), make_double2((double)k, (double)k));
+    }
+}
+
 int grid_for(size_t n, int block)
 {
     int dev = 0, sms = 148;
@@ -147,6 +168,18 @@ int ppx_cuda_fill_uniform(double *out, size_t count, uint64_t seed, uint64_t fir
     if (!out)
         return PPX_ERR_BAD_ARGUMENT;
     k_fill_uniform<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(out, count, seed, first, lo, hi);
+    g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaPeekAtLastError();
+}
+
+int ppx_cuda_probe_write(double *out, int planes, size_t n, size_t ld, int mode, void *stream)
+{
+    if (!out || planes < 1 || ld < n)
+        return PPX_ERR_BAD_ARGUMENT;
+    if (mode == 0)
+        k_probe_write<0><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(out, planes, n, ld);
+    else
+        k_probe_write<1><<<grid_for(n / 2, 256), 256, 0, (cudaStream_t)stream>>>(out, planes, n, ld);
     g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaPeekAtLastError();
 }

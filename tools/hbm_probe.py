@@ -17,3 +17,16 @@ s = t(lambda: z.zero_()); print(f"write only        {z.numel()*4/s/1e9:8.1f} GB/
 s = t(lambda: z.fill_(1.5)); print(f"fill  only        {z.numel()*4/s/1e9:8.1f} GB/s")
 r = torch.empty(n, dtype=torch.float32, device="cuda")
 s = t(lambda: r.sum()); print(f"read only (sum)   {r.numel()*4/s/1e9:8.1f} GB/s")
+
+# the store pattern of the SoA batch kernels in isolation
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from matrix_b200._lib import lib, check
+n = 1 << 24
+for planes in (1, 9, 16, 36, 52):
+    buf = torch.empty((planes, n), dtype=torch.float64, device="cuda")
+    for mode in (0, 1):
+        s = t(lambda: check(lib.ppx_cuda_probe_write(C.c_void_p(buf.data_ptr()), planes, n, n, mode,
+                                                     C.c_void_p(torch.cuda.current_stream().cuda_stream))))
+        print(f"SoA write, {planes:2d} planes, {'128' if mode else ' 64'}-bit stores: {planes*n*8/s/1e9:8.1f} GB/s")
+    del buf
