@@ -82,6 +82,22 @@ struct OpFkJacobian
     }
 };
 
+// dq = linsolve<SVD>(Js, Vs).x: a square Jacobian (6 joints) takes the row-orthogonalising solve that needs no V
+template <int NJ>
+__device__ __forceinline__ typename std::enable_if<NJ == 6>::type svd_solve_dispatch(double (&js)[36], const double (&vs)[6],
+                                                                                    double (&dq)[6])
+{
+    jacobi_rowsolve<6>(js, vs, dq);
+}
+template <int NJ>
+__device__ __forceinline__ typename std::enable_if<NJ != 6>::type svd_solve_dispatch(double (&js)[6 * NJ],
+                                                                                    const double (&vs)[6], double (&dq)[NJ])
+{
+    double V[NJ * NJ], w2[NJ];
+    jacobi_svd_core<6, NJ, true>(js, V, w2);
+    jacobi_svd_solve<6, NJ>(js, V, w2, vs, dq);
+}
+
 // Vs = Ad(T(q)) log(T(q)^-1 Tt),  dq = pinv(Js(q)) Vs  (test/lie_test.cpp:104-110)
 template <int NJ>
 __device__ __forceinline__ void ik_newton_update(const ChainConst<NJ> &ch, const Rigid &target, double (&q)[NJ],
@@ -100,9 +116,8 @@ __device__ __forceinline__ void ik_newton_update(const ChainConst<NJ> &ch, const
     SE3_log(x, lg);
     const double lw[3] = {lg[0], lg[1], lg[2]}, lv[3] = {lg[3], lg[4], lg[5]};
     rigid_adjoint_apply(t, lw, lv, vs);
-    double V[NJ * NJ], w2[NJ], dq[NJ];
-    jacobi_svd_core<6, NJ, true>(js, V, w2);
-    jacobi_svd_solve<6, NJ>(js, V, w2, vs, dq);
+    double dq[NJ];
+    svd_solve_dispatch<NJ>(js, vs, dq);
 #pragma unroll
     for (int i = 0; i < NJ; i++)
         q[i] += dq[i];

@@ -750,8 +750,9 @@ PPX_DEV void swap_cols(double (&xp)[L], double (&xq)[L])
 }
 
 // One round of the odd-even ordering: positions (START, START+1), (START+2, START+3), ...
-template <int M, int N, int START, bool WANT_V>
-PPX_DEV void svd_round(double (&a)[N][M], double (&v)[N][N], double (&nrm)[N], double tol2, bool &rotated)
+template <int M, int N, int START, bool WANT_V, bool WANT_C>
+PPX_DEV void svd_round(double (&a)[N][M], double (&v)[N][N], double (&cv)[N], double (&nrm)[N], double tol2,
+                       bool &rotated)
 {
     constexpr int P = (N - START) / 2;
     double c[P > 0 ? P : 1], s[P > 0 ? P : 1];
@@ -772,6 +773,12 @@ PPX_DEV void svd_round(double (&a)[N][M], double (&v)[N][N], double (&nrm)[N], d
         rotate_swap<M>(a[START + 2 * k], a[START + 2 * k + 1], c[k], s[k]);
         if (WANT_V)
             rotate_swap<N>(v[START + 2 * k], v[START + 2 * k + 1], c[k], s[k]);
+        if (WANT_C) // a vector with one entry per column, carried through the same rotations
+        {
+            const double x = cv[START + 2 * k], y = cv[START + 2 * k + 1];
+            cv[START + 2 * k] = fma(s[k], x, c[k] * y);
+            cv[START + 2 * k + 1] = fma(c[k], x, -s[k] * y);
+        }
     }
 }
 
@@ -790,10 +797,13 @@ PPX_DEV void svd_round(double (&a)[N][M], double (&v)[N][N], double (&nrm)[N], d
 // sqrt(M) eps; the singular values come out with relative accuracy ~ tol).  Sweeps stop when a whole sweep
 // rotated nothing in any lane of the warp.  Squared column norms are recomputed at the start of every sweep and
 // carried through its rotations (a rotation by tangent t moves t*gamma from one norm to the other).
-template <int M, int N, bool WANT_V>
-PPX_DEV void jacobi_svd_core(double (&A)[M * N], double (&V)[N * N], double (&w2)[N])
+template <int M, int N, bool WANT_V, bool WANT_C = false>
+PPX_DEV void jacobi_svd_core(double (&A)[M * N], double (&V)[N * N], double (&w2)[N], double *carry = nullptr)
 {
-    double a[N][M], v[N][N], nrm[N];
+    double a[N][M], v[N][N], nrm[N], cv[N];
+#pragma unroll
+    for (int j = 0; j < N; j++)
+        cv[j] = WANT_C ? carry[j] : 0.0;
 #pragma unroll
     for (int j = 0; j < N; j++)
     {
@@ -822,11 +832,11 @@ PPX_DEV void jacobi_svd_core(double (&A)[M * N], double (&V)[N * N], double (&w2
 #pragma unroll 1
         for (int it = 0; it < N / 2; it++)
         {
-            svd_round<M, N, 0, WANT_V>(a, v, nrm, TOL2, rotated);
-            svd_round<M, N, 1, WANT_V>(a, v, nrm, TOL2, rotated);
+            svd_round<M, N, 0, WANT_V, WANT_C>(a, v, cv, nrm, TOL2, rotated);
+            svd_round<M, N, 1, WANT_V, WANT_C>(a, v, cv, nrm, TOL2, rotated);
         }
         if (N & 1)
-            svd_round<M, N, 0, WANT_V>(a, v, nrm, TOL2, rotated);
+            svd_round<M, N, 0, WANT_V, WANT_C>(a, v, cv, nrm, TOL2, rotated);
         reversed = !reversed;
         if (!__any_sync(0xffffffffu, rotated))
             break;
@@ -850,6 +860,8 @@ PPX_DEV void jacobi_svd_core(double (&A)[M * N], double (&V)[N * N], double (&w2
             for (int i = 0; i < N; i++)
                 V[i + j * N] = reversed ? v[N - 1 - j][i] : v[j][i];
         }
+        if (WANT_C)
+            carry[j] = reversed ? cv[N - 1 - j] : cv[j];
     }
 }
 
@@ -879,6 +891,42 @@ PPX_DEV void jacobi_svd_solve(const double (&A)[M * N], const double (&V)[N * N]
 #pragma unroll
         for (int i = 0; i < N; i++)
             x[i] = fma(V[i + j * N], coef, x[i]);
+    }
+}
+
+// Truncated pseudo-inverse solve of a SQUARE system without accumulating V (or U): orthogonalise the ROWS of A with the
+// same Jacobi machinery (columns of A^T) and carry b through the rotations.  With G = U^T A (orthogonal rows g_j of
+// norm w_j) and c = U^T b,  A^+ b = G^T diag(1/w^2) c = sum_j g_j c_j / w_j^2  over w_j > tsh -- the same truncation as
+// SVD::solve (linalg.hpp:886-913), 64 instead of 88 fp64 instructions per rotation.
+template <int N>
+PPX_DEV void jacobi_rowsolve(const double (&A)[N * N], const double (&b)[N], double (&x)[N])
+{
+    double At[N * N], dummy[N * N], w2[N], c[N];
+#pragma unroll
+    for (int r = 0; r < N; r++)
+    {
+        c[r] = b[r];
+#pragma unroll
+        for (int j = 0; j < N; j++)
+            At[j + r * N] = A[r + j * N];
+    }
+    jacobi_svd_core<N, N, false, true>(At, dummy, w2, c);
+    double wmax2 = w2[0];
+#pragma unroll
+    for (int j = 1; j < N; j++)
+        wmax2 = fmax(wmax2, w2[j]);
+    const double f = 0.5 * sqrt((double)(2 * N + 1)) * EPS_DP;
+    const double tsh2 = f * f * wmax2;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        x[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; j++)
+    {
+        const double coef = w2[j] > tsh2 ? c[j] / w2[j] : 0.0;
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            x[i] = fma(At[i + j * N], coef, x[i]);
     }
 }
 

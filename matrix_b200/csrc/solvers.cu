@@ -77,6 +77,22 @@ struct OpSVD
     }
 };
 
+// square systems: row-orthogonalising solve (no V); rectangular ones: column Jacobi with V
+template <int N>
+__device__ __forceinline__ void solve_scaled(double (&a)[N * N], double (&)[N * N], double (&)[N], const double (&rhs)[N],
+                                             double (&sol)[N])
+{
+    jacobi_rowsolve<N>(a, rhs, sol);
+}
+template <int M, int N>
+__device__ __forceinline__ typename std::enable_if<M != N>::type solve_scaled(double (&a)[M * N], double (&v)[N * N],
+                                                                             double (&w2)[N], const double (&rhs)[M],
+                                                                             double (&sol)[N])
+{
+    jacobi_svd_core<M, N, true>(a, v, w2);
+    jacobi_svd_solve<M, N>(a, v, w2, rhs, sol);
+}
+
 template <int M, int N>
 struct OpLinsolveSVD
 {
@@ -92,8 +108,7 @@ struct OpLinsolveSVD
         io.load(b, rhs);
         const int shift = pow2_shift(a);
         pow2_rescale(a, shift);
-        jacobi_svd_core<M, N, true>(a, v, w2);
-        jacobi_svd_solve<M, N>(a, v, w2, rhs, sol);
+        solve_scaled(a, v, w2, rhs, sol);
         pow2_rescale(sol, shift); // (A 2^-shift)^+ b = 2^shift A^+ b
         io.store(x, sol);
     }
