@@ -52,6 +52,32 @@ def measured_peaks():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def gpu_local_cpus(device_index):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None: pinned buffers allocated by a thread running there land
+    in memory one PCIe hop from the device -- a remote node can cost the host-buffer path most of its PCIe rate."""
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id  # not available on every torch build
+    except Exception:
+        bdf = None
+    try:
+        if bdf is None:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i",
+                                  str(device_index)], capture_output=True, text=True).stdout.strip()
+            bdf = out.lower().replace("00000000:", "0000:")
+        node = int(open(f"/sys/bus/pci/devices/{str(bdf).lower()}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -299,6 +325,10 @@ def main():
             n_e2e //= 2
         del w.T, w.Js  # free device outputs of the kernel-only leg
         torch.cuda.empty_cache()
+        all_cpus = os.sched_getaffinity(0)
+        near = gpu_local_cpus(local)
+        if near:
+            os.sched_setaffinity(0, near)  # allocate (first-touch) the pinned buffers on the GPU's NUMA node
         h2d, d2h = w.host_setup(n_e2e)
         # raw pinned-copy rates of this box: the ceiling of any host-buffer path
         probe_h = torch.empty(1 << 28, dtype=torch.uint8, pin_memory=True)
@@ -328,6 +358,8 @@ def main():
                "ms_per_step": dt / args.e2e_steps * 1e3, "api": "ppx_cuda_host_poe_fk_jacobian (pinned host AoS)",
                "pcie_gbs": (h2d + d2h) * args.e2e_steps / dt / 1e9, "pcie_h2d_gbs_measured": pcie["h2d"],
                "pcie_d2h_gbs_measured": pcie["d2h"], "result_probe": loss}
+        e2e["numa_bound"] = bool(near)
+        os.sched_setaffinity(0, all_cpus)
         for k in ("hq", "hT", "hJ"):
             if hasattr(w, k):
                 delattr(w, k)
