@@ -9,40 +9,12 @@
 #include <cmath>
 
 #include "ppx_launch.cuh"
+#include "ppx_codo.cuh"
 
 using namespace ppx_dev;
 
 namespace
 {
-
-template <int NJ>
-void fold_chain(const double *screws, const double *home, ChainConst<NJ> &ch)
-{
-    for (int i = 0; i < NJ; i++)
-    {
-        JointConst &j = ch.joint[i];
-        const double *s = screws + 6 * i;
-        for (int k = 0; k < 3; k++)
-        {
-            j.w[k] = s[k];
-            j.v[k] = s[3 + k];
-        }
-        j.wv[0] = j.w[1] * j.v[2] - j.w[2] * j.v[1];
-        j.wv[1] = j.w[2] * j.v[0] - j.w[0] * j.v[2];
-        j.wv[2] = j.w[0] * j.v[1] - j.w[1] * j.v[0];
-        j.wwv[0] = j.w[1] * j.wv[2] - j.w[2] * j.wv[1];
-        j.wwv[1] = j.w[2] * j.wv[0] - j.w[0] * j.wv[2];
-        j.wwv[2] = j.w[0] * j.wv[1] - j.w[1] * j.wv[0];
-        j.wn = std::sqrt(j.w[0] * j.w[0] + j.w[1] * j.w[1] + j.w[2] * j.w[2]);
-        j.iw = j.wn > 0.0 ? 1.0 / j.wn : 0.0;
-        j.iw2 = j.iw * j.iw;
-        j.iw3 = j.iw2 * j.iw;
-    }
-    for (int c = 0; c < 3; c++)
-        for (int r = 0; r < 3; r++)
-            ch.home_r[r + 3 * c] = home[r + 4 * c];
-    ch.home_p[0] = home[12], ch.home_p[1] = home[13], ch.home_p[2] = home[14];
-}
 
 // BASELINE config 2.  48 B in, 128 + 288 B out per instance at NJ = 6: write-dominated and HBM-bound.
 template <int NJ, bool WANT_T, bool WANT_J>
@@ -204,394 +176,12 @@ struct OpIkSolve
 };
 
 // ------------------------------------------------------------------------------------------------
-// kinematics<6>::inverseSpace(pose, init) of demo/robotics.hpp:126-152 -- the bounded trust-region
-// dogleg details::CoDo<6,6> (include/optimization.hpp:497-829) on f(q) = log(T(q) pose^-1) with the analytic Jacobian
-// [[I,0],[-hat(p),I]] Js(q) of robotics.hpp:134-140 and the joints' ranges as the box.  One instance per thread: the
-// iteration counts are data dependent, so a warp runs as long as its slowest lane (no warp-level collectives inside).
-template <int NJ>
-struct CodoProblem
-{
-    const ChainConst<NJ> &ch;
-    Rigid poseI; // pose^-1
-    // f and df are deliberately NOT inlined: the optimiser calls f from three places, and one copy of the kinematics
-    // keeps the iteration body inside the instruction cache (ncu: `no_instruction` was the top stall when inlined)
-    __device__ __noinline__ void f(const double (&q)[NJ], double (&fx)[6]) const
-    {
-        Rigid t, x;
-        poe_fk_jacobian<NJ, true, false>(ch, q, t, [](int, const double(&)[6]) {});
-        rigid_mul(t, poseI, x);
-        SE3_log(x, fx);
-    }
-    // column j of [[I,0],[-hat(p),I]] Js = (w_j ; v_j - p x w_j), p = translation of T(q) pose^-1
-    __device__ __noinline__ void df(const double (&q)[NJ], double (&jac)[6 * NJ]) const
-    {
-        Rigid t, x;
-        poe_fk_jacobian<NJ, true, true>(ch, q, t, [&](int col, const double(&v)[6]) {
-#pragma unroll
-            for (int k = 0; k < 6; k++)
-                jac[6 * col + k] = v[k];
-        });
-        rigid_mul(t, poseI, x);
-#pragma unroll
-        for (int j = 0; j < NJ; j++)
-        {
-            const double w[3] = {jac[6 * j], jac[6 * j + 1], jac[6 * j + 2]};
-            double c[3];
-            cross3(x.p, w, c);
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-                jac[6 * j + 3 + k] -= c[k];
-        }
-    }
-};
-
-__device__ __forceinline__ double norm6(const double (&v)[6])
-{
-    double a = 0.0;
-#pragma unroll
-    for (int i = 0; i < 6; i++)
-        a = fma(v[i], v[i], a);
-    return sqrt(a);
-}
-__device__ __forceinline__ double dot6(const double (&a)[6], const double (&b)[6])
-{
-    double r = 0.0;
-#pragma unroll
-    for (int i = 0; i < 6; i++)
-        r = fma(a[i], b[i], r);
-    return r;
-}
-__device__ __forceinline__ void matvec6(const double (&A)[36], const double (&x)[6], double (&y)[6])
-{
-#pragma unroll
-    for (int i = 0; i < 6; i++)
-    {
-        double a = 0.0;
-#pragma unroll
-        for (int k = 0; k < 6; k++)
-            a = fma(A[i + 6 * k], x[k], a);
-        y[i] = a;
-    }
-}
-__device__ __forceinline__ double min6(const double (&v)[6])
-{
-    double m = v[0];
-#pragma unroll
-    for (int i = 1; i < 6; i++)
-        m = fmin(m, v[i]);
-    return m;
-}
-
-// CoDo<6,6>::operator() (optimization.hpp:542-779) with DMatrixCi (:787-808): same constants, same tests, same order
-// of decisions -- written as a state machine (codo_init + one codo_step per trip of the optimiser's while loop) so that
-// a lane whose instance has finished can pick up the next instance instead of idling until the slowest lane of its
-// warp is done (trip counts range from 3 to ITMAX = 300; ncu on the plain per-thread loop: 5.4 of 32 lanes active).
-struct CodoState
-{
-    double x[6], fx[6], grad[6], p[6];
-    double fnrm, delta0, y;
-    unsigned itc;
-    int stat;
-};
-
-constexpr double CODO_MAX_SP = 3.4028234663852886e+38; // MAX_SP, include/exprtmpl.hpp:14
-
-// -> true when the instance is already finished (illegal start, :546-556)
-__device__ __forceinline__ bool codo_init(const CodoProblem<6> &pb, const double (&lo)[6], const double (&hi)[6],
-                                          CodoState &st)
-{
-    bool legal = true;
-#pragma unroll
-    for (int i = 0; i < 6; i++)
-    {
-        legal = legal && lo[i] <= st.x[i] && st.x[i] <= hi[i];
-        st.grad[i] = 0.0;
-        st.p[i] = 0.0;
-    }
-    st.itc = 0;
-    st.delta0 = 1.0;
-    st.stat = PPX_STATUS_CONVERGED;
-    if (!legal)
-    {
-        st.y = CODO_MAX_SP;
-        st.stat = PPX_STATUS_DIVERGED;
-        return true;
-    }
-    pb.f(st.x, st.fx);
-    st.fnrm = norm6(st.fx);
-    st.y = 0.5 * st.fnrm;
-    return false;
-}
-
-// one trip of `while (fnrm > FTOLA && itc++ < ITMAX)` (:567-776) -> true when the optimiser is done
-__device__ __forceinline__ bool codo_step(const CodoProblem<6> &pb, const double (&lo)[6], const double (&hi)[6],
-                                          CodoState &st)
-{
-    constexpr double MAX_SP = CODO_MAX_SP, sigma = 0.99995, theta = 0.99995, FTOLA = EPS_SP;
-    constexpr unsigned ITMAX = 300;
-    double(&x)[6] = st.x;
-    double(&fx)[6] = st.fx;
-    double(&grad)[6] = st.grad;
-    double(&p)[6] = st.p;
-    double &fnrm = st.fnrm;
-    double &delta0 = st.delta0;
-    const double sqrt_eps = sqrt(EPS_DP);
-    if (!(fnrm > FTOLA && st.itc++ < ITMAX))
-    {
-        st.y = 0.5 * fnrm;
-        return true;
-    }
-    const unsigned itc = st.itc;
-    {
-        const double fnrm_old = fnrm;
-        double grad_old[6], jac[36], tmp[6], d[6], dsqrt[6], G[6], dgrad[6], pc[6], pn[6];
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-            grad_old[i] = grad[i];
-        pb.df(x, jac);
-#pragma unroll
-        for (int i = 0; i < 6; i++) // grad = jac^T fx
-        {
-            double a = 0.0;
-#pragma unroll
-            for (int k = 0; k < 6; k++)
-                a = fma(jac[k + 6 * i], fx[k], a);
-            grad[i] = a;
-        }
-        double lambda;
-        if (itc == 1)
-            lambda = fmax(1e-2, norm6(grad));
-        else
-        {
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-                tmp[i] = grad[i] - grad_old[i];
-            lambda = fmax(1e-2, dot6(p, tmp) / dot6(p, p));
-        }
-#pragma unroll
-        for (int i = 0; i < 6; i++) // Hager scaling, :787-808
-        {
-            if (grad[i] < 0.0 && hi[i] <= MAX_SP)
-                d[i] = 1.0 / (lambda - grad[i] / (hi[i] - x[i]));
-            else if (grad[i] > 0.0 && lo[i] >= -MAX_SP)
-                d[i] = 1.0 / (lambda + grad[i] / (x[i] - lo[i]));
-            else
-                d[i] = 1.0 / lambda;
-        }
-        if (min6(d) < EPS_DP)
-        {
-            st.stat = PPX_STATUS_DIVERGED;
-            st.y = 0.5 * fnrm;
-            return true;
-        }
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-        {
-            dsqrt[i] = sqrt(d[i]);
-            G[i] = 1.0 / dsqrt[i];
-            dgrad[i] = d[i] * grad[i];
-            tmp[i] = G[i] * dgrad[i];
-        }
-        const double nGdgrad = norm6(tmp);
-        if (norm6(dgrad) < FTOLA)
-        {
-            st.y = 0.5 * fnrm;
-            return true;
-        }
-        double jd[6];
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-            tmp[i] = dsqrt[i] * grad[i];
-        matvec6(jac, dgrad, jd);
-        const double ratio = norm6(tmp) / norm6(jd);
-        const double vert = ratio * ratio;
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-            pc[i] = -vert * dgrad[i];
-        if (itc == 1)
-        {
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-                tmp[i] = grad[i] / G[i];
-            delta0 = norm6(tmp);
-        }
-        // projected Newton step through LU with partial pivoting (linsolve<Factorization::LU>, :608)
-        double lu[36], rx[6];
-#pragma unroll
-        for (int i = 0; i < 36; i++)
-            lu[i] = jac[i];
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-            rx[i] = fx[i];
-        bool even;
-        const bool singular = lu_factor_solve<6, 1>(lu, rx, even);
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-            pn[i] = singular ? -fx[i] : -rx[i];
-        if (!singular)
-        {
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-                pn[i] = fmax(x[i] + pn[i], lo[i]) - x[i];
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-                pn[i] = fmin(x[i] + pn[i], hi[i]) - x[i];
-            const double sc = fmax(sigma, 1.0 - norm6(pn));
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-                pn[i] *= sc;
-        }
-        // trust-region loop, :620-727
-        double rho = 0.0, delta1 = delta0, xp[6], fxp[6], fxpnrm = 0.0;
-        bool again;
-        do
-        {
-            double pciv[6], alp[6];
-            const bool cauchy = vert * nGdgrad > delta1;
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-                pciv[i] = cauchy ? -delta1 / nGdgrad * dgrad[i] : pc[i];
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-                alp[i] = fabs(pciv[i]) < EPS_DP ? MAX_SP : fmax((lo[i] - x[i]) / pciv[i], (hi[i] - x[i]) / pciv[i]);
-            double alpha1 = min6(alp);
-            if (alpha1 <= 1.0)
-            {
-                const double sc = fmax(theta, 1.0 - norm6(pciv)) * alpha1;
-#pragma unroll
-                for (int i = 0; i < 6; i++)
-                    pciv[i] *= sc;
-            }
-            if (!singular)
-            {
-                double aa[6], seg[6], bb[6], jp[6];
-                matvec6(jac, pciv, jp);
-#pragma unroll
-                for (int i = 0; i < 6; i++)
-                {
-                    aa[i] = fx[i] + jp[i];
-                    seg[i] = pn[i] - pciv[i];
-                }
-                matvec6(jac, seg, bb);
-                double gamma = 0.0;
-                if (norm6(bb) != 0.0)
-                {
-                    const double gamma_min = -dot6(aa, bb) / dot6(bb, bb);
-                    double Gseg[6], Gpciv[6];
-#pragma unroll
-                    for (int i = 0; i < 6; i++)
-                    {
-                        Gseg[i] = G[i] * seg[i];
-                        Gpciv[i] = G[i] * pciv[i];
-                    }
-                    const double a = dot6(Gseg, Gseg); // SQR(norm2(.))
-                    const double b = dot6(Gpciv, Gseg);
-                    const double c = dot6(Gpciv, Gpciv) - delta1 * delta1;
-                    const double root = sqrt(b * b - a * c);
-                    const double l1 = (-b + (-b >= 0.0 ? fabs(root) : -fabs(root))) / a;
-                    const double l2 = c / (l1 * a);
-                    if (gamma_min > 0.0)
-                    {
-                        gamma = fmin(gamma_min, fmax(l1, l2));
-                        if (gamma > 1.0)
-                        {
-#pragma unroll
-                            for (int i = 0; i < 6; i++)
-                                alp[i] = seg[i] != 0.0 ? fmax((lo[i] - x[i] - pciv[i]) / seg[i], (hi[i] - x[i] - pciv[i]) / seg[i])
-                                                       : MAX_SP;
-                            gamma = fmin(theta * min6(alp), gamma);
-                        }
-                    }
-                    else
-                    {
-                        gamma = fmax(gamma_min, fmin(l1, l2));
-                        if (gamma < 0.0)
-                        {
-#pragma unroll
-                            for (int i = 0; i < 6; i++)
-                                alp[i] = seg[i] != 0.0 ? fmax((x[i] + pciv[i] - lo[i]) / seg[i], (x[i] + pciv[i] - hi[i]) / seg[i])
-                                                       : MAX_SP;
-                            gamma = fmax(-theta * min6(alp), gamma);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 6; i++)
-                    p[i] = (1.0 - gamma) * pciv[i] + gamma * pn[i];
-            }
-            else
-            {
-#pragma unroll
-                for (int i = 0; i < 6; i++)
-                    p[i] = pciv[i];
-            }
-            double jp2[6], lin[6], Gp[6];
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-                xp[i] = x[i] + p[i];
-            pb.f(xp, fxp);
-            fxpnrm = norm6(fxp);
-            matvec6(jac, p, jp2);
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-            {
-                lin[i] = fx[i] + jp2[i];
-                Gp[i] = G[i] * p[i];
-            }
-            rho = (fnrm - fxpnrm) / (fnrm - norm6(lin));
-            again = false;
-            if (rho < 0.25)
-            {
-                delta1 = fmin(0.25 * delta0, 0.5 * norm6(Gp));
-                again = delta1 > sqrt_eps;
-            }
-            else if (rho > 0.75)
-                delta0 = fmax(delta1, 2.0 * norm6(Gp)); // :735-738 (only reached when the loop ends here)
-        } while (again);
-        if (rho < 0.25 && delta1 < sqrt_eps)
-        {
-            st.stat = PPX_STATUS_DIVERGED;
-            st.y = 0.5 * fnrm;
-            return true;
-        }
-        bool need_update = false;
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-        {
-            x[i] = xp[i];
-            if (x[i] < lo[i] + 1e3 * EPS_DP)
-            {
-                x[i] = lo[i] + 1e3 * EPS_DP;
-                need_update = true;
-            }
-            if (x[i] > hi[i] - 1e3 * EPS_DP)
-            {
-                x[i] = hi[i] - 1e3 * EPS_DP;
-                need_update = true;
-            }
-        }
-        if (need_update)
-        {
-            pb.f(x, fx);
-            fnrm = norm6(fx);
-        }
-        else
-        {
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-                fx[i] = fxp[i];
-            fnrm = fxpnrm;
-        }
-        st.y = 0.5 * fnrm;
-        if (fabs(fnrm - fnrm_old) < FTOLA * fnrm && fnrm > FTOLA)
-            return true;
-    }
-    return false;
-}
-
-// Persistent warps with per-lane work refill: every lane owns one instance at a time and, when its optimiser
-// finishes, claims the next unprocessed instance from a global counter (one atomicAdd per warp per refill round).
-// All lanes of a warp then execute the same codo_step in lockstep, each on its own instance.
+// kinematics<6>::inverseSpace(pose, init) of demo/robotics.hpp:126-152.  The optimiser itself is the
+// state machine of ppx_codo.cuh; this kernel feeds it.
+//
+// Persistent warps with per-lane work refill: every lane owns one instance at a time and, when its optimiser returns,
+// claims the next unprocessed instance from a global counter (one atomicAdd per warp per refill round).  Each trip of
+// the loop is one evaluation of residual + Jacobian for all 32 lanes, whatever phase of the optimiser they are in.
 struct IkCodoArgs
 {
     ChainConst<6> ch;
@@ -618,16 +208,30 @@ __device__ __forceinline__ void rec_put(double *base, size_t i, int k, int width
         __stcs(base + (size_t)k * ld + i, v);
 }
 
+// One CTA of 8 warps per SM, and the warps of the CTA start every trip together (PPX_CODO_ALIGN): the body of a trip is
+// ~60 KB of instructions, twice the SM's instruction cache, so warps that drift apart evict each other's code and the
+// kernel ends up waiting for instruction fetches (2/3 of all cycles in the unaligned first version, profiles/); warps
+// that walk through the code side by side share every fetched line.
+#ifndef PPX_CODO_BLOCK
+#define PPX_CODO_BLOCK 256
+#endif
+#ifndef PPX_CODO_MINB
+#define PPX_CODO_MINB 1
+#endif
+#ifndef PPX_CODO_ALIGN
+#define PPX_CODO_ALIGN 1
+#endif
+
 template <int LAYOUT>
-__global__ void __launch_bounds__(128, 2) ik_codo_kernel(const __grid_constant__ IkCodoArgs a, size_t n, size_t ld,
-                                                        unsigned long long *next)
+__global__ void __launch_bounds__(PPX_CODO_BLOCK, PPX_CODO_MINB)
+    ik_codo_kernel(const __grid_constant__ IkCodoArgs a, size_t n, size_t ld, unsigned long long *next)
 {
     const unsigned lane = threadIdx.x & 31;
-    CodoProblem<6> pb{a.ch, Rigid()};
-    CodoState st;
+    CodoLane st;
+    Rigid poseI; // pose^-1
     double q0[6];
     size_t idx = 0;
-    bool busy = false, fresh = false;
+    bool busy = false, finished = false;
     for (;;)
     {
         // refill: lanes without work claim consecutive instances
@@ -655,43 +259,45 @@ __global__ void __launch_bounds__(128, 2) ik_codo_kernel(const __grid_constant__
                     }
                     Rigid pose;
                     rigid_from_record(m, pose);
-                    rigid_inv(pose, pb.poseI);
+                    rigid_inv(pose, poseI);
                     busy = true;
-                    fresh = true;
+                    finished = codo_begin(a.lo, a.hi, st);
                 }
             }
         }
+#if PPX_CODO_ALIGN
+        if (!__syncthreads_or(busy)) // also the barrier that lines the warps up
+            break;
+#else
         if (!__any_sync(0xffffffffu, busy))
             break;
-        if (busy)
+#endif
+        if (busy && !finished)
         {
-            bool done = false;
-            if (fresh)
-            {
-                done = codo_init(pb, a.lo, a.hi, st);
-                fresh = false;
-            }
-            if (!done)
-                done = codo_step(pb, a.lo, a.hi, st);
-            if (done)
-            {
+            double fp[6], jp[36];
+            codo_eval<6>(a.ch, poseI, st.probe, fp, jp);
+            finished = codo_advance(a.lo, a.hi, st, fp, jp);
+        }
+        if (busy && finished)
+        {
 #pragma unroll
-                for (int k = 0; k < 6; k++)
-                {
-                    // inverseSpace returns the optimiser's x only if CONVERGED, else init (robotics.hpp:151)
-                    rec_put<LAYOUT>(a.q_out, idx, k, 6, ld, st.stat == PPX_STATUS_CONVERGED ? st.x[k] : q0[k]);
-                    if (a.x_raw != nullptr)
-                        rec_put<LAYOUT>(a.x_raw, idx, k, 6, ld, st.x[k]);
-                }
-                if (a.fnorm != nullptr)
-                    a.fnorm[idx] = st.y;
-                if (a.status != nullptr)
-                    a.status[idx] = (int8_t)st.stat;
-                busy = false;
+            for (int k = 0; k < 6; k++)
+            {
+                // inverseSpace returns the optimiser's x only if CONVERGED, else init (robotics.hpp:151)
+                rec_put<LAYOUT>(a.q_out, idx, k, 6, ld, st.stat == PPX_STATUS_CONVERGED ? st.x[k] : q0[k]);
+                if (a.x_raw != nullptr)
+                    rec_put<LAYOUT>(a.x_raw, idx, k, 6, ld, st.x[k]);
             }
+            if (a.fnorm != nullptr)
+                a.fnorm[idx] = st.y;
+            if (a.status != nullptr)
+                a.status[idx] = (int8_t)st.stat;
+            busy = false;
+            finished = false;
         }
     }
 }
+
 template <int NJ>
 int fk_jacobian_n(const double *screws, const double *home, const double *q, double *T, double *Js, size_t n,
                   int layout, size_t ld, void *stream)
@@ -821,10 +427,10 @@ int ppx_cuda_batch_ik_codo(const double *screws, const double *home, int njoints
     cudaMemsetAsync(next, 0, sizeof(*next), s);
     auto kern = layout == PPX_LAYOUT_AOS ? ik_codo_kernel<LAYOUT_AOS> : ik_codo_kernel<LAYOUT_SOA>;
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);
-    const size_t want = (n + 127) / 128;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PPX_CODO_BLOCK, 0);
+    const size_t want = (n + PPX_CODO_BLOCK - 1) / PPX_CODO_BLOCK;
     const size_t cap = (size_t)info.sms * (per_sm > 0 ? per_sm : 1);
-    kern<<<(unsigned)(want < cap ? want : cap), 128, 0, s>>>(a, n, ld, next);
+    kern<<<(unsigned)(want < cap ? want : cap), PPX_CODO_BLOCK, 0, s>>>(a, n, ld, next);
     g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);
     e = cudaPeekAtLastError();
     cudaFreeAsync(next, s);

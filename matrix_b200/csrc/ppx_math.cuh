@@ -369,6 +369,36 @@ struct ChainConst
     double home_p[3];
 };
 
+// Host side: everything about the chain that does not depend on the instance (done once per call).
+template <int NJ>
+inline void fold_chain(const double *screws, const double *home, ChainConst<NJ> &ch)
+{
+    for (int i = 0; i < NJ; i++)
+    {
+        JointConst &j = ch.joint[i];
+        const double *s = screws + 6 * i;
+        for (int k = 0; k < 3; k++)
+        {
+            j.w[k] = s[k];
+            j.v[k] = s[3 + k];
+        }
+        j.wv[0] = j.w[1] * j.v[2] - j.w[2] * j.v[1];
+        j.wv[1] = j.w[2] * j.v[0] - j.w[0] * j.v[2];
+        j.wv[2] = j.w[0] * j.v[1] - j.w[1] * j.v[0];
+        j.wwv[0] = j.w[1] * j.wv[2] - j.w[2] * j.wv[1];
+        j.wwv[1] = j.w[2] * j.wv[0] - j.w[0] * j.wv[2];
+        j.wwv[2] = j.w[0] * j.wv[1] - j.w[1] * j.wv[0];
+        j.wn = sqrt(j.w[0] * j.w[0] + j.w[1] * j.w[1] + j.w[2] * j.w[2]);
+        j.iw = j.wn > 0.0 ? 1.0 / j.wn : 0.0;
+        j.iw2 = j.iw * j.iw;
+        j.iw3 = j.iw2 * j.iw;
+    }
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++)
+            ch.home_r[r + 3 * c] = home[r + 4 * c];
+    ch.home_p[0] = home[12], ch.home_p[1] = home[13], ch.home_p[2] = home[14];
+}
+
 // exp(S q) for a fixed screw S = (w; v) and a per-instance angle q (se3::exp of `JList[i].screw * q`,
 // demo/robotics.hpp:88-89).  With x = |w| q:
 //   R = I + (sin x/|w|) W + ((1-cos x)/|w|^2) W^2,  p = q v + ((1-cos x)/|w|^2) (w x v) + ((x - sin x)/|w|^3) (w x (w x v))
@@ -520,14 +550,22 @@ PPX_DEV int linsolve_qr(double (&A)[M * N], double (&b)[M], double (&x)[N])
 PPX_DEV double rsqrt_nr(double x)
 {
     double y;
+#ifdef __CUDA_ARCH__
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+    y = (double)(float)(1.0 / sqrt(x)); // host build of the device math (tests/cpp/codo_host.cpp): a seed of the same quality
+#endif
     const double e = fma(-(x * y), y, 1.0); // 1 - x y^2
     return fma(y * e, fma(0.375, e, 0.5), y); // y (1 + e/2 + 3 e^2/8)
 }
 PPX_DEV double rcp_nr(double x)
 {
     double y;
+#ifdef __CUDA_ARCH__
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+    y = (double)(float)(1.0 / x);
+#endif
     const double e = fma(-x, y, 1.0); // 1 - x y
     return fma(y, fma(e, e, e), y);   // y (1 + e + e^2)
 }
