@@ -410,12 +410,14 @@ def main():
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "instances_per_gpu": n, "layout": "soa (device resident)",
-                       "chain": "UR5 (test/lie_test.cpp:187-196)" if "ur5" in args.workload or "ik" in args.workload
+                       "chain": "UR5 (test/lie_test.cpp:187-196)" if "ur5" in args.workload or "ik" in args.workload or "inverse" in args.workload
                        else None,
                        "l2": f"inputs+outputs {n * cls.bytes_per_instance() / 1e6:.0f} MB per step >> 126 MB L2, "
                              "evict-first loads/stores", "parallelism": f"instance-sharded x{world}, no collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks.summary(), "fp64_peak_tflops_measured": fp64_peak, "other_workloads": others,
+            "clocks": clocks.summary(), "fp64_peak_tflops_measured": fp64_peak,
+            "step_ms": {"min": min(per_step), "median": statistics.median(per_step), "max": max(per_step)},
+            "other_workloads": others,
         }
         print(json.dumps(out))
     if world > 1:

@@ -228,6 +228,8 @@ __global__ void __launch_bounds__(PPX_CODO_BLOCK, PPX_CODO_MINB)
 {
     const unsigned lane = threadIdx.x & 31;
     CodoLane st;
+    double jbuf[72];
+    st.jbuf = jbuf;
     Rigid poseI; // pose^-1
     double q0[6];
     size_t idx = 0;
@@ -272,11 +274,12 @@ __global__ void __launch_bounds__(PPX_CODO_BLOCK, PPX_CODO_MINB)
         if (!__any_sync(0xffffffffu, busy))
             break;
 #endif
+        const unsigned active = __ballot_sync(0xffffffffu, busy && !finished);
         if (busy && !finished)
         {
-            double fp[6], jp[36];
-            codo_eval<6>(a.ch, poseI, st.probe, fp, jp);
-            finished = codo_advance(a.lo, a.hi, st, fp, jp);
+            double fp[6];
+            codo_eval<6>(a.ch, poseI, st.probe, fp, codo_jac_probe(st));
+            finished = codo_advance(active, a.lo, a.hi, st, fp);
         }
         if (busy && finished)
         {

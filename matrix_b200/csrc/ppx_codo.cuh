@@ -2,7 +2,7 @@
 // the bounded trust-region dogleg details::CoDo<6,6> (include/optimization.hpp:497-829) on f(q) = log(T(q) pose^-1)
 // with the analytic Jacobian [[I,0],[-hat(p),I]] Js(q) of robotics.hpp:134-140 and the joints' ranges as the box.
 //
-// Shape of the code (what the first version of this kernel got wrong, profiles/r1g_ncu_codo.txt):
+// Shape of the code (what the first version of this kernel got wrong, profiles/r1gh_ncu_inverse_space_codo.txt):
 //   * The optimiser's control flow is data dependent (3 .. 300 trips of its while loop, each with an inner
 //     trust-region loop), so it is written as a STATE MACHINE around one evaluation: every trip of the device loop
 //     evaluates residual and Jacobian at the lane's `probe` point -- the start, a trial point x + p, or the clamped
@@ -151,7 +151,10 @@ enum CodoPhase
 
 struct CodoLane
 {
-    double x[6], fx[6], jac[36]; // iterate, residual and Jacobian there
+    double x[6], fx[6];  // iterate and residual there
+    double *jbuf;        // -> 2 x 36 doubles owned by the caller (kept apart so that the rest of the state can live in
+                         // registers): the Jacobian at x is jbuf[36 cur ..], the evaluation at `probe` writes the other
+    int cur;             // half, and accepting a trial point is a flip of `cur`
     double probe[6];             // where the next evaluation happens
     double grad[6], p[6];        // carried from trip to trip (Barzilai-Borwein lambda, :574-583)
     double pc[6], pn[6], dgrad[6], G[6]; // of the running trip; needed again every time the trust region shrinks
@@ -160,6 +163,9 @@ struct CodoLane
     int stat, phase;
     bool singular;
 };
+
+PPX_DEV const double *codo_jac(const CodoLane &s) { return s.jbuf + 36 * s.cur; }
+PPX_DEV double *codo_jac_probe(CodoLane &s) { return s.jbuf + 36 * (s.cur ^ 1); }
 
 // after x was set: false -> evaluate at probe; true -> finished (illegal start, :546-556)
 PPX_DEV bool codo_begin(const double (&lo)[6], const double (&hi)[6], CodoLane &s)
@@ -174,6 +180,7 @@ PPX_DEV bool codo_begin(const double (&lo)[6], const double (&hi)[6], CodoLane &
         s.probe[i] = s.x[i];
     }
     s.itc = 0;
+    s.cur = 0;
     s.delta0 = 1.0;
     s.stat = PPX_STATUS_CONVERGED;
     s.phase = CODO_START;
@@ -186,24 +193,31 @@ PPX_DEV bool codo_begin(const double (&lo)[6], const double (&hi)[6], CodoLane &
     return false;
 }
 
-// (fp, jp) = residual and Jacobian at s.probe.  Does what the reference does up to its next evaluation and leaves the
-// point of that evaluation in s.probe; -> true when the optimiser has returned (s.x, s.y, s.stat are its result).
-PPX_DEV bool codo_advance(const double (&lo)[6], const double (&hi)[6], CodoLane &s, const double (&fp)[6],
-                          const double *jp)
+// The optimiser between two evaluations, in three stages.  Which stages a lane runs depends on its phase and on the
+// outcome of the trial, so the lanes of a warp part ways; codo_advance() brings them back together before every stage
+// (without that, lanes that reach a stage over different paths would execute it one group after the other).
+enum CodoNext
 {
-    constexpr double MAX_SP = CODO_MAX_SP, sigma = 0.99995, theta = 0.99995, FTOLA = EPS_SP;
-    constexpr unsigned ITMAX = 300;
+    CODO_EVAL = 0, // nothing more to do before the next evaluation
+    CODO_DONE = 1, // the optimiser has returned: s.x, s.y, s.stat are its result
+    CODO_HEAD = 2, // start the next trip
+    CODO_BUILD = 4 // build the dogleg step for the current trust-region radius
+};
+
+// stage 1: fp and codo_jac_probe(s) = residual and Jacobian at s.probe have arrived
+PPX_DEV unsigned codo_judge(const double (&lo)[6], const double (&hi)[6], CodoLane &s, const double (&fp)[6])
+{
+    constexpr double FTOLA = EPS_SP;
     constexpr double sqrt_eps = 1.4901161193847656e-08; // sqrt(EPS_DP), exact
     double(&x)[6] = s.x;
     double(&fx)[6] = s.fx;
-    bool tail = false, head = false, build = false;
-
+    double fnew;
     if (s.phase == CODO_TRIAL)
     {
         // judge the trial point, :705-727
         const double fxpnrm = codo_norm6(fp);
         double jp2[6], lin[6], Gp[6];
-        codo_matvec(s.jac, s.p, jp2);
+        codo_matvec(codo_jac(s), s.p, jp2);
 #pragma unroll
         for (int i = 0; i < 6; i++)
         {
@@ -211,86 +225,74 @@ PPX_DEV bool codo_advance(const double (&lo)[6], const double (&hi)[6], CodoLane
             Gp[i] = s.G[i] * s.p[i];
         }
         const double rho = codo_div(s.fnrm - fxpnrm, s.fnrm - codo_norm6(lin));
-        bool again = false;
         if (rho < 0.25)
         {
             s.delta1 = fmin(0.25 * s.delta0, 0.5 * codo_norm6(Gp));
-            again = s.delta1 > sqrt_eps;
-        }
-        else if (rho > 0.75)
-            s.delta0 = fmax(s.delta1, 2.0 * codo_norm6(Gp)); // :735-738
-        if (again)
-            build = true;
-        else
-        {
-            if (rho < 0.25 && s.delta1 < sqrt_eps)
+            if (s.delta1 > sqrt_eps)
+                return CODO_BUILD; // same trip, smaller trust region
+            if (s.delta1 < sqrt_eps)
             {
                 s.stat = PPX_STATUS_DIVERGED;
                 s.y = 0.5 * s.fnrm;
-                return true;
+                return CODO_DONE;
             }
-            // accept, then keep the iterate strictly inside the box (:747-762)
-            bool need_update = false;
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-            {
-                double xi = s.probe[i];
-                if (xi < lo[i] + 1e3 * EPS_DP)
-                {
-                    xi = lo[i] + 1e3 * EPS_DP;
-                    need_update = true;
-                }
-                if (xi > hi[i] - 1e3 * EPS_DP)
-                {
-                    xi = hi[i] - 1e3 * EPS_DP;
-                    need_update = true;
-                }
-                x[i] = xi;
-                s.probe[i] = xi;
-            }
-            if (need_update)
-            {
-                s.phase = CODO_CLAMPED;
-                return false;
-            }
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-                fx[i] = fp[i];
-#pragma unroll
-            for (int i = 0; i < 36; i++)
-                s.jac[i] = jp[i];
-            s.fnrm = fxpnrm;
-            tail = true;
         }
-    }
-    else
-    {
+        else if (rho > 0.75)
+            s.delta0 = fmax(s.delta1, 2.0 * codo_norm6(Gp)); // :735-738
+        // accept, then keep the iterate strictly inside the box (:747-762)
+        bool need_update = false;
 #pragma unroll
         for (int i = 0; i < 6; i++)
-            fx[i] = fp[i];
+        {
+            double xi = s.probe[i];
+            if (xi < lo[i] + 1e3 * EPS_DP)
+            {
+                xi = lo[i] + 1e3 * EPS_DP;
+                need_update = true;
+            }
+            if (xi > hi[i] - 1e3 * EPS_DP)
+            {
+                xi = hi[i] - 1e3 * EPS_DP;
+                need_update = true;
+            }
+            x[i] = xi;
+            s.probe[i] = xi;
+        }
+        if (need_update)
+        {
+            s.phase = CODO_CLAMPED; // the reference evaluates f again at the clamped point
+            return CODO_EVAL;
+        }
+        fnew = fxpnrm;
+    }
+    else
+        fnew = codo_norm6(fp);
+    // residual and Jacobian at the probe belong to the iterate now
 #pragma unroll
-        for (int i = 0; i < 36; i++)
-            s.jac[i] = jp[i];
-        s.fnrm = codo_norm6(fx);
-        s.y = 0.5 * s.fnrm;
-        tail = s.phase == CODO_CLAMPED;
-        head = !tail;
-    }
-    if (tail)
+    for (int i = 0; i < 6; i++)
+        fx[i] = fp[i];
+    s.cur ^= 1;
+    s.fnrm = fnew;
+    s.y = 0.5 * fnew;
+    // end of a trip, :764-775 (not after the very first evaluation)
+    if (s.phase != CODO_START && fabs(s.fnrm - s.fnrm_old) < FTOLA * s.fnrm && s.fnrm > FTOLA)
+        return CODO_DONE;
+    return CODO_HEAD;
+}
+
+// stage 2: `while (fnrm > FTOLA && itc++ < ITMAX)` and the trip up to its trust-region loop, :567-618
+PPX_DEV unsigned codo_trip_head(const double (&lo)[6], const double (&hi)[6], CodoLane &s)
+{
+    constexpr double MAX_SP = CODO_MAX_SP, sigma = 0.99995, FTOLA = EPS_SP;
+    constexpr unsigned ITMAX = 300;
+    double(&x)[6] = s.x;
+    double(&fx)[6] = s.fx;
+    const double *jac = codo_jac(s);
     {
-        // end of a trip, :764-775
-        s.y = 0.5 * s.fnrm;
-        if (fabs(s.fnrm - s.fnrm_old) < FTOLA * s.fnrm && s.fnrm > FTOLA)
-            return true;
-        head = true;
-    }
-    if (head)
-    {
-        // `while (fnrm > FTOLA && itc++ < ITMAX)` and the trip up to its trust-region loop, :567-618
         if (!(s.fnrm > FTOLA && s.itc++ < ITMAX))
         {
             s.y = 0.5 * s.fnrm;
-            return true;
+            return CODO_DONE;
         }
         s.fnrm_old = s.fnrm;
         double grad_new[6], tmp[6], d[6], dsqrt[6];
@@ -300,7 +302,7 @@ PPX_DEV bool codo_advance(const double (&lo)[6], const double (&hi)[6], CodoLane
             double a = 0.0;
 #pragma unroll
             for (int k = 0; k < 6; k++)
-                a = fma(s.jac[k + 6 * i], fx[k], a);
+                a = fma(jac[k + 6 * i], fx[k], a);
             grad_new[i] = a;
         }
         double lambda;
@@ -330,7 +332,7 @@ PPX_DEV bool codo_advance(const double (&lo)[6], const double (&hi)[6], CodoLane
         {
             s.stat = PPX_STATUS_DIVERGED;
             s.y = 0.5 * s.fnrm;
-            return true;
+            return CODO_DONE;
         }
 #pragma unroll
         for (int i = 0; i < 6; i++)
@@ -344,13 +346,13 @@ PPX_DEV bool codo_advance(const double (&lo)[6], const double (&hi)[6], CodoLane
         if (codo_norm6(s.dgrad) < FTOLA)
         {
             s.y = 0.5 * s.fnrm;
-            return true;
+            return CODO_DONE;
         }
         double jd[6];
 #pragma unroll
         for (int i = 0; i < 6; i++)
             tmp[i] = dsqrt[i] * s.grad[i];
-        codo_matvec(s.jac, s.dgrad, jd);
+        codo_matvec(jac, s.dgrad, jd);
         const double ratio = codo_div(codo_norm6(tmp), codo_norm6(jd));
         s.vert = ratio * ratio;
 #pragma unroll
@@ -367,7 +369,7 @@ PPX_DEV bool codo_advance(const double (&lo)[6], const double (&hi)[6], CodoLane
         double lu[36], rx[6];
 #pragma unroll
         for (int i = 0; i < 36; i++)
-            lu[i] = s.jac[i];
+            lu[i] = jac[i];
 #pragma unroll
         for (int i = 0; i < 6; i++)
             rx[i] = fx[i];
@@ -390,11 +392,18 @@ PPX_DEV bool codo_advance(const double (&lo)[6], const double (&hi)[6], CodoLane
                 s.pn[i] *= sc;
         }
         s.delta1 = s.delta0;
-        build = true;
     }
-    if (build)
+    return CODO_BUILD;
+}
+
+// stage 3: the dogleg step inside the trust region of radius delta1, :622-703; its end point is the next probe
+PPX_DEV void codo_build(const double (&lo)[6], const double (&hi)[6], CodoLane &s)
+{
+    constexpr double MAX_SP = CODO_MAX_SP, theta = 0.99995;
+    double(&x)[6] = s.x;
+    double(&fx)[6] = s.fx;
+    const double *jac = codo_jac(s);
     {
-        // the dogleg step inside the trust region of radius delta1, :622-703
         double pciv[6], alp[6];
         const bool cauchy = s.vert * s.nGdgrad > s.delta1;
         const double shrink = -codo_div(s.delta1, s.nGdgrad);
@@ -418,14 +427,14 @@ PPX_DEV bool codo_advance(const double (&lo)[6], const double (&hi)[6], CodoLane
         if (!s.singular)
         {
             double aa[6], seg[6], bb[6], jpc[6];
-            codo_matvec(s.jac, pciv, jpc);
+            codo_matvec(jac, pciv, jpc);
 #pragma unroll
             for (int i = 0; i < 6; i++)
             {
                 aa[i] = fx[i] + jpc[i];
                 seg[i] = s.pn[i] - pciv[i];
             }
-            codo_matvec(s.jac, seg, bb);
+            codo_matvec(jac, seg, bb);
             double gamma = 0.0;
             const double bb2 = codo_dot6(bb, bb);
             if (bb2 != 0.0) // norm2(bb) != 0
@@ -476,7 +485,28 @@ PPX_DEV bool codo_advance(const double (&lo)[6], const double (&hi)[6], CodoLane
             s.probe[i] = x[i] + s.p[i];
         s.phase = CODO_TRIAL;
     }
-    return false;
+}
+
+#ifdef __CUDA_ARCH__
+#define PPX_CODO_CONVERGE(mask) __syncwarp(mask)
+#else
+#define PPX_CODO_CONVERGE(mask) ((void)(mask))
+#endif
+
+// fp and codo_jac_probe(s) = residual and Jacobian at s.probe.  Does what the reference does up to its next evaluation
+// and leaves the point of that evaluation in s.probe; -> true when the optimiser has returned (s.x, s.y, s.stat are its
+// result).  `lanes` = the lanes of the warp that make this call together.
+PPX_DEV bool codo_advance(unsigned lanes, const double (&lo)[6], const double (&hi)[6], CodoLane &s,
+                          const double (&fp)[6])
+{
+    unsigned next = codo_judge(lo, hi, s, fp);
+    PPX_CODO_CONVERGE(lanes);
+    if (next & CODO_HEAD)
+        next = codo_trip_head(lo, hi, s);
+    PPX_CODO_CONVERGE(lanes);
+    if (next & CODO_BUILD)
+        codo_build(lo, hi, s);
+    return (next & CODO_DONE) != 0;
 }
 
 } // namespace ppx_dev

@@ -57,6 +57,8 @@ extern "C" int codo_host_run(const double *screws, const double *home, const dou
     for (size_t idx = 0; idx < n; idx++)
     {
         CodoLane st;
+        double jbuf[72];
+        st.jbuf = jbuf;
         double m[16], q0[6];
         std::memcpy(m, Tt + 16 * idx, sizeof(m));
         for (int k = 0; k < 6; k++)
@@ -68,10 +70,10 @@ extern "C" int codo_host_run(const double *screws, const double *home, const dou
         int count = 0;
         while (!finished)
         {
-            double fp[6], jp[36];
-            codo_eval<6>(ch, poseI, st.probe, fp, jp);
+            double fp[6];
+            codo_eval<6>(ch, poseI, st.probe, fp, codo_jac_probe(st));
             count++;
-            finished = codo_advance(blo, bhi, st, fp, jp);
+            finished = codo_advance(1u, blo, bhi, st, fp);
         }
         for (int k = 0; k < 6; k++)
         {
