@@ -120,60 +120,118 @@ struct OpIkStep
     }
 };
 
-// The whole loop of test/lie_test.cpp:96-113: the convergence test uses the Vs of the current step
-// and the update of that step is still applied, exactly as the reference does.  A warp keeps
-// iterating while any of its lanes is unconverged; converged lanes stop updating.
-template <int NJ>
-struct OpIkSolve
+// dense-record / component-plane access for the persistent kernels below (one instance per lane, claimed at run time)
+template <int LAYOUT>
+__device__ __forceinline__ double rec_get(const double *base, size_t i, int k, int width, size_t ld)
 {
-    static constexpr int BLOCK = 128, MINB = 1, MAXW = 16;
-    ChainConst<NJ> ch;
+    return LAYOUT == LAYOUT_AOS ? __ldcs(base + i * width + k) : __ldcs(base + (size_t)k * ld + i);
+}
+template <int LAYOUT>
+__device__ __forceinline__ void rec_put(double *base, size_t i, int k, int width, size_t ld, double v)
+{
+    if (LAYOUT == LAYOUT_AOS)
+        __stcs(base + i * width + k, v);
+    else
+        __stcs(base + (size_t)k * ld + i, v);
+}
+
+// lanes of a warp without work claim consecutive unprocessed instances from a global counter: one atomicAdd per warp
+// and refill round.  -> the claimed index (>= n: nothing left); call with the whole warp converged.
+__device__ __forceinline__ size_t claim_instances(bool wants, unsigned long long *next)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned want = __ballot_sync(0xffffffffu, wants);
+    if (want == 0)
+        return ~(size_t)0;
+    const int leader = __ffs(want) - 1;
+    unsigned long long first = 0;
+    if ((int)lane == leader)
+        first = atomicAdd(next, (unsigned long long)__popc(want));
+    first = __shfl_sync(0xffffffffu, first, leader);
+    return wants ? (size_t)first + __popc(want & ((1u << lane) - 1)) : ~(size_t)0;
+}
+
+// The whole loop of test/lie_test.cpp:96-113: the convergence test uses the Vs of the current step and the update of
+// that step is still applied, exactly as the reference does.  Iteration counts differ from target to target (3 .. 20,
+// mean 4.1 on the bench workload, but 7.3 for the slowest lane of a warp), so the kernel is persistent with per-lane
+// refill: a lane whose instance has stopped stores it and takes the next one; every trip of the loop is one Newton step
+// of all 32 lanes.  The step contains warp votes (Jacobi sweep termination), so lanes without work run it too, on the
+// instance they finished last.
+struct IkSolveArgs
+{
+    ChainConst<6> ch;
     const double *q0;
     const double *Tt;
     double *q_out;
     int32_t *iters;
     int8_t *status;
     int max_iter;
-    template <class IO>
-    __device__ __forceinline__ void operator()(const IO &io) const
+};
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(128, 1)
+    ik_solve_kernel(const __grid_constant__ IkSolveArgs a, size_t n, size_t ld, unsigned long long *next)
+{
+    constexpr int NJ = 6;
+    double qi[NJ], vs[6];
+    Rigid target;
+    rigid_identity(target);
+#pragma unroll
+    for (int k = 0; k < NJ; k++)
+        qi[k] = 0.25 * (k + 1); // a regular configuration for lanes that never get work
+    size_t idx = 0;
+    int it = 0;
+    bool busy = false, finished = false, conv = false;
+    for (;;)
     {
-        double qi[NJ], m[16], vs[6];
-        Rigid target;
-        io.load(q0, qi);
-        io.load(Tt, m);
-        rigid_from_record(m, target);
-        bool done = !io.valid;
-        int it = 0;
-        for (int k = 0; k < max_iter; k++)
+        const size_t got = claim_instances(!busy, next);
+        if (!busy && got < n)
         {
-            if (__all_sync(0xffffffffu, done))
-                break;
-            double qn[NJ];
+            idx = got;
+            double m[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                m[k] = rec_get<LAYOUT>(a.Tt, idx, k, 16, ld);
+#pragma unroll
+            for (int k = 0; k < NJ; k++)
+                qi[k] = rec_get<LAYOUT>(a.q0, idx, k, NJ, ld);
+            rigid_from_record(m, target);
+            busy = true;
+            it = 0;
+            conv = false;
+            finished = a.max_iter == 0;
+        }
+        if (!__any_sync(0xffffffffu, busy))
+            break;
+        double qn[NJ];
+#pragma unroll
+        for (int i = 0; i < NJ; i++)
+            qn[i] = qi[i];
+        ik_newton_update<NJ>(a.ch, target, qn, vs);
+        if (busy && !finished)
+        {
 #pragma unroll
             for (int i = 0; i < NJ; i++)
-                qn[i] = qi[i];
-            ik_newton_update<NJ>(ch, target, qn, vs);
-            if (!done)
-            {
-#pragma unroll
-                for (int i = 0; i < NJ; i++)
-                    qi[i] = qn[i];
-                it++;
-                const double ew = sqrt(fma(vs[2], vs[2], fma(vs[1], vs[1], vs[0] * vs[0])));
-                const double ev = sqrt(fma(vs[5], vs[5], fma(vs[4], vs[4], vs[3] * vs[3])));
-                done = ew < EPS_SP && ev < EPS_SP;
-            }
+                qi[i] = qn[i];
+            it++;
+            const double ew = sqrt(fma(vs[2], vs[2], fma(vs[1], vs[1], vs[0] * vs[0])));
+            const double ev = sqrt(fma(vs[5], vs[5], fma(vs[4], vs[4], vs[3] * vs[3])));
+            conv = ew < EPS_SP && ev < EPS_SP;
+            finished = conv || it >= a.max_iter;
         }
-        io.store(q_out, qi);
-        if (io.valid)
+        if (busy && finished)
         {
-            if (iters != nullptr)
-                iters[io.i] = it;
-            if (status != nullptr)
-                status[io.i] = done ? PPX_STATUS_CONVERGED : PPX_STATUS_DIVERGED;
+#pragma unroll
+            for (int k = 0; k < NJ; k++)
+                rec_put<LAYOUT>(a.q_out, idx, k, NJ, ld, qi[k]);
+            if (a.iters != nullptr)
+                a.iters[idx] = it;
+            if (a.status != nullptr)
+                a.status[idx] = conv ? PPX_STATUS_CONVERGED : PPX_STATUS_DIVERGED;
+            busy = false;
         }
     }
-};
+}
 
 // ------------------------------------------------------------------------------------------------
 // kinematics<6>::inverseSpace(pose, init) of demo/robotics.hpp:126-152.  The optimiser itself is the
@@ -194,20 +252,6 @@ struct IkCodoArgs
     int8_t *status;
 };
 
-template <int LAYOUT>
-__device__ __forceinline__ double rec_get(const double *base, size_t i, int k, int width, size_t ld)
-{
-    return LAYOUT == LAYOUT_AOS ? __ldcs(base + i * width + k) : __ldcs(base + (size_t)k * ld + i);
-}
-template <int LAYOUT>
-__device__ __forceinline__ void rec_put(double *base, size_t i, int k, int width, size_t ld, double v)
-{
-    if (LAYOUT == LAYOUT_AOS)
-        __stcs(base + i * width + k, v);
-    else
-        __stcs(base + (size_t)k * ld + i, v);
-}
-
 // One CTA of 8 warps per SM, and the warps of the CTA start every trip together (PPX_CODO_ALIGN): the body of a trip is
 // ~60 KB of instructions, twice the SM's instruction cache, so warps that drift apart evict each other's code and the
 // kernel ends up waiting for instruction fetches (2/3 of all cycles in the unaligned first version, profiles/); warps
@@ -226,7 +270,6 @@ template <int LAYOUT>
 __global__ void __launch_bounds__(PPX_CODO_BLOCK, PPX_CODO_MINB)
     ik_codo_kernel(const __grid_constant__ IkCodoArgs a, size_t n, size_t ld, unsigned long long *next)
 {
-    const unsigned lane = threadIdx.x & 31;
     CodoLane st;
     double jbuf[72];
     st.jbuf = jbuf;
@@ -237,35 +280,25 @@ __global__ void __launch_bounds__(PPX_CODO_BLOCK, PPX_CODO_MINB)
     for (;;)
     {
         // refill: lanes without work claim consecutive instances
-        const unsigned want = __ballot_sync(0xffffffffu, !busy);
-        if (want)
+        const size_t got = claim_instances(!busy, next);
+        if (!busy && got < n)
         {
-            unsigned long long first = 0;
-            if (lane == (unsigned)(__ffs(want) - 1))
-                first = atomicAdd(next, (unsigned long long)__popc(want));
-            first = __shfl_sync(0xffffffffu, first, __ffs(want) - 1);
-            if (!busy)
+            idx = got;
+            double m[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                m[k] = rec_get<LAYOUT>(a.Tt, idx, k, 16, ld);
+#pragma unroll
+            for (int k = 0; k < 6; k++)
             {
-                idx = (size_t)first + __popc(want & ((1u << lane) - 1));
-                if (idx < n)
-                {
-                    double m[16];
-#pragma unroll
-                    for (int k = 0; k < 16; k++)
-                        m[k] = rec_get<LAYOUT>(a.Tt, idx, k, 16, ld);
-#pragma unroll
-                    for (int k = 0; k < 6; k++)
-                    {
-                        q0[k] = rec_get<LAYOUT>(a.init, idx, k, 6, ld);
-                        st.x[k] = q0[k];
-                    }
-                    Rigid pose;
-                    rigid_from_record(m, pose);
-                    rigid_inv(pose, poseI);
-                    busy = true;
-                    finished = codo_begin(a.lo, a.hi, st);
-                }
+                q0[k] = rec_get<LAYOUT>(a.init, idx, k, 6, ld);
+                st.x[k] = q0[k];
             }
+            Rigid pose;
+            rigid_from_record(m, pose);
+            rigid_inv(pose, poseI);
+            busy = true;
+            finished = codo_begin(a.lo, a.hi, st);
         }
 #if PPX_CODO_ALIGN
         if (!__syncthreads_or(busy)) // also the barrier that lines the warps up
@@ -323,13 +356,31 @@ int ik_step_n(const double *screws, const double *home, const double *q, const d
     return dispatch(layout, OpIkStep<NJ>{ch, q, Tt, q_out, Vs}, n, ld, stream);
 }
 
-template <int NJ>
-int ik_solve_n(const double *screws, const double *home, const double *q0, const double *Tt, int max_iter,
-               double *q_out, int32_t *iters, int8_t *status, size_t n, int layout, size_t ld, void *stream)
+// Launch of a persistent kernel with a work counter: as many CTAs as are resident at once; the counter lives for this
+// launch only (stream-ordered allocation, zeroed on the stream).
+template <class Kernel, class Args>
+int launch_persistent(Kernel kern, int block, const Args &a, size_t n, size_t ld, void *stream)
 {
-    ChainConst<NJ> ch;
-    fold_chain<NJ>(screws, home, ch);
-    return dispatch(layout, OpIkSolve<NJ>{ch, q0, Tt, q_out, iters, status, max_iter}, n, ld, stream);
+    DeviceInfo info;
+    int device = 0;
+    int rc = device_info(info, device);
+    if (rc != PPX_OK)
+        return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long *next = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&next, sizeof(*next), s);
+    if (e != cudaSuccess)
+        return (int)e;
+    cudaMemsetAsync(next, 0, sizeof(*next), s);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);
+    const size_t want = (n + block - 1) / block;
+    const size_t cap = (size_t)info.sms * (per_sm > 0 ? per_sm : 1);
+    kern<<<(unsigned)(want < cap ? want : cap), block, 0, s>>>(a, n, ld, next);
+    g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);
+    e = cudaPeekAtLastError();
+    cudaFreeAsync(next, s);
+    return (int)e;
 }
 
 } // namespace
@@ -392,7 +443,15 @@ int ppx_cuda_batch_ik_solve(const double *screws, const double *home, int njoint
     if (n == 0)
         return PPX_OK;
     PPX_CHECK_PTRS(screws, home, q0, Ttarget, q_out);
-    return ik_solve_n<6>(screws, home, q0, Ttarget, max_iter, q_out, iters, status, n, layout, ld, stream);
+    if (layout != PPX_LAYOUT_AOS && layout != PPX_LAYOUT_SOA)
+        return PPX_ERR_BAD_LAYOUT;
+    if (layout == PPX_LAYOUT_SOA && ld < n)
+        return PPX_ERR_BAD_ARGUMENT;
+    IkSolveArgs a;
+    fold_chain<6>(screws, home, a.ch);
+    a.q0 = q0, a.Tt = Ttarget, a.q_out = q_out, a.iters = iters, a.status = status, a.max_iter = max_iter;
+    return layout == PPX_LAYOUT_AOS ? launch_persistent(ik_solve_kernel<LAYOUT_AOS>, 128, a, n, ld, stream)
+                                    : launch_persistent(ik_solve_kernel<LAYOUT_SOA>, 128, a, n, ld, stream);
 }
 
 int ppx_cuda_batch_ik_codo(const double *screws, const double *home, int njoints, const double *lo, const double *hi,
@@ -416,28 +475,8 @@ int ppx_cuda_batch_ik_codo(const double *screws, const double *home, int njoints
         a.hi[i] = hi[i];
     }
     a.Tt = Ttarget, a.init = init, a.q_out = q_out, a.x_raw = x_raw, a.fnorm = fnorm, a.status = status;
-    DeviceInfo info;
-    int device = 0;
-    int rc = device_info(info, device);
-    if (rc != PPX_OK)
-        return rc;
-    cudaStream_t s = (cudaStream_t)stream;
-    // the work counter lives for this launch only (stream-ordered allocation, zeroed on the stream)
-    unsigned long long *next = nullptr;
-    cudaError_t e = cudaMallocAsync((void **)&next, sizeof(*next), s);
-    if (e != cudaSuccess)
-        return (int)e;
-    cudaMemsetAsync(next, 0, sizeof(*next), s);
-    auto kern = layout == PPX_LAYOUT_AOS ? ik_codo_kernel<LAYOUT_AOS> : ik_codo_kernel<LAYOUT_SOA>;
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PPX_CODO_BLOCK, 0);
-    const size_t want = (n + PPX_CODO_BLOCK - 1) / PPX_CODO_BLOCK;
-    const size_t cap = (size_t)info.sms * (per_sm > 0 ? per_sm : 1);
-    kern<<<(unsigned)(want < cap ? want : cap), PPX_CODO_BLOCK, 0, s>>>(a, n, ld, next);
-    g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);
-    e = cudaPeekAtLastError();
-    cudaFreeAsync(next, s);
-    return (int)e;
+    return layout == PPX_LAYOUT_AOS ? launch_persistent(ik_codo_kernel<LAYOUT_AOS>, PPX_CODO_BLOCK, a, n, ld, stream)
+                                    : launch_persistent(ik_codo_kernel<LAYOUT_SOA>, PPX_CODO_BLOCK, a, n, ld, stream);
 }
 
 } // extern "C"
