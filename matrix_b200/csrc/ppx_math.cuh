@@ -740,17 +740,22 @@ struct Tournament
     __host__ __device__ static constexpr bool valid(int r, int k) { return hi(r, k) < N; }
 };
 
+// cos^2 of the angle between two columns below which a rotation counts as "fine" (see jacobi_svd_core's look-ahead)
+constexpr double SVD_FINE_COS2 = 1e-10;
+
 // One rotation of the one-sided Jacobi SVD on the columns at positions p and p+1, derived in two phases so that
 // the rotations of a round (disjoint positions) can be derived together: their chains are independent and overlap.
 template <int M>
 PPX_DEV void svd_pair_derive(const double (&ap)[M], const double (&aq)[M], double &np_, double &nq_, double tol2,
-                             double &c, double &s, bool &act)
+                             double &c, double &s, bool &act, bool &coarse)
 {
     double ga = 0.0;
 #pragma unroll
     for (int i = 0; i < M; i++)
         ga = fma(ap[i], aq[i], ga);
-    act = ga * ga > tol2 * (np_ * nq_);
+    const double g2 = ga * ga, nn = np_ * nq_;
+    act = g2 > tol2 * nn;
+    coarse |= g2 > SVD_FINE_COS2 * nn;
     double t;
     jacobi_cst(np_, nq_, ga, c, s, t);
     c = act ? c : 1.0;
@@ -790,7 +795,7 @@ PPX_DEV void swap_cols(double (&xp)[L], double (&xq)[L])
 // One round of the odd-even ordering: positions (START, START+1), (START+2, START+3), ...
 template <int M, int N, int START, bool WANT_V, bool WANT_C>
 PPX_DEV void svd_round(double (&a)[N][M], double (&v)[N][N], double (&cv)[N], double (&nrm)[N], double tol2,
-                       bool &rotated)
+                       bool &rotated, bool &coarse)
 {
     constexpr int P = (N - START) / 2;
     double c[P > 0 ? P : 1], s[P > 0 ? P : 1];
@@ -799,7 +804,7 @@ PPX_DEV void svd_round(double (&a)[N][M], double (&v)[N][N], double (&cv)[N], do
     for (int k = 0; k < P; k++)
     {
         svd_pair_derive<M>(a[START + 2 * k], a[START + 2 * k + 1], nrm[START + 2 * k], nrm[START + 2 * k + 1], tol2,
-                           c[k], s[k], act[k]);
+                           c[k], s[k], act[k], coarse);
         rotated |= act[k];
     }
 #pragma unroll
@@ -866,18 +871,52 @@ PPX_DEV void jacobi_svd_core(double (&A)[M * N], double (&V)[N * N], double (&w2
                 a2 = fma(a[j][i], a[j][i], a2);
             nrm[j] = a2;
         }
-        bool rotated = false;
+        bool rotated = false, coarse = false;
 #pragma unroll 1
         for (int it = 0; it < N / 2; it++)
         {
-            svd_round<M, N, 0, WANT_V, WANT_C>(a, v, cv, nrm, TOL2, rotated);
-            svd_round<M, N, 1, WANT_V, WANT_C>(a, v, cv, nrm, TOL2, rotated);
+            svd_round<M, N, 0, WANT_V, WANT_C>(a, v, cv, nrm, TOL2, rotated, coarse);
+            svd_round<M, N, 1, WANT_V, WANT_C>(a, v, cv, nrm, TOL2, rotated, coarse);
         }
         if (N & 1)
-            svd_round<M, N, 0, WANT_V, WANT_C>(a, v, cv, nrm, TOL2, rotated);
+            svd_round<M, N, 0, WANT_V, WANT_C>(a, v, cv, nrm, TOL2, rotated, coarse);
         reversed = !reversed;
         if (!__any_sync(0xffffffffu, rotated))
             break;
+#ifndef PPX_SVD_NO_LOOKAHEAD
+        // Look-ahead.  Convergence is quadratic, so a sweep whose rotations were all fine (cos < 1e-5) is nearly
+        // always the last one that rotates, and the sweep after it would only establish that: N(N-1)/2 pairs derived
+        // and "rotated" by the identity.  The same test -- every pair within tolerance, norms fresh -- costs a quarter
+        // of that when made directly.  It is exactly the decision the next sweep would take (no rotation happens in
+        // it, so the order in which it meets the pairs does not matter), hence the results are bit-identical.
+        if (!__any_sync(0xffffffffu, coarse))
+        {
+            double n2[N];
+#pragma unroll
+            for (int j = 0; j < N; j++)
+            {
+                double a2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < M; i++)
+                    a2 = fma(a[j][i], a[j][i], a2);
+                n2[j] = a2;
+            }
+            bool clean = true;
+#pragma unroll
+            for (int p = 0; p < N; p++)
+#pragma unroll
+                for (int q = p + 1; q < N; q++)
+                {
+                    double ga = 0.0;
+#pragma unroll
+                    for (int i = 0; i < M; i++)
+                        ga = fma(a[p][i], a[q][i], ga);
+                    clean = clean && !(ga * ga > TOL2 * (n2[p] * n2[q]));
+                }
+            if (__all_sync(0xffffffffu, clean))
+                break;
+        }
+#endif
     }
     // an odd number of sweeps leaves the columns in reverse order: undo it (the sweep count is warp-uniform)
 #pragma unroll

@@ -37,6 +37,7 @@ static inline double __hiloint2double(int hi, int lo)
     return x;
 }
 static inline int __any_sync(unsigned, int p) { return p; }
+static inline int __all_sync(unsigned, int p) { return p; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 
