@@ -20,7 +20,10 @@ namespace
 template <int NJ, bool WANT_T, bool WANT_J>
 struct OpFkJacobian
 {
-    static constexpr int BLOCK = 128, MINB = 4, MAXW = (WANT_J ? 6 * NJ : 16) > 16 ? (WANT_J ? 6 * NJ : 16) : 16;
+#ifndef PPX_FK_MINB
+#define PPX_FK_MINB 4
+#endif
+    static constexpr int BLOCK = 128, MINB = PPX_FK_MINB, MAXW = (WANT_J ? 6 * NJ : 16) > 16 ? (WANT_J ? 6 * NJ : 16) : 16;
     ChainConst<NJ> ch;
     const double *q;
     double *T;

@@ -649,6 +649,80 @@ PPX_DEV bool lu_factor_solve(double (&A)[N * N], double (&B)[N * (NRHS > 0 ? NRH
     return singular;
 }
 
+// MatrixS::I() (include/linalg.hpp:933-948: LU with partial pivoting, then one solve per unit vector; {} when SINGULAR)
+// as an in-place Gauss-Jordan elimination with the same pivoting: the candidates for pivot k are the entries the LU
+// sees (eliminating above the diagonal does not touch rows >= k), so the pivot sequence and the SINGULAR decision are
+// the reference's, and the inverse overwrites A -- 36 live doubles for n = 6 instead of 72 for "factor + 6 right-hand
+// sides", which is what lets this HBM-bound kernel run 4 CTAs per SM instead of 2.  Row exchanges are predicated swaps
+// (compile-time indices only); they come back as column exchanges of the result, last first: A^-1 = (P A)^-1 P.
+template <int N>
+PPX_DEV bool gauss_jordan_inverse(double (&A)[N * N])
+{
+    bool singular = false;
+    int piv[N];
+#pragma unroll
+    for (int k = 0; k < N; k++)
+    {
+        double valmax = fabs(A[k + k * N]);
+        int ip = k;
+#pragma unroll
+        for (int r = k + 1; r < N; r++)
+        {
+            const double t = fabs(A[r + k * N]);
+            const bool better = valmax < t;
+            valmax = better ? t : valmax;
+            ip = better ? r : ip;
+        }
+        singular |= valmax < EPS_DP;
+        piv[k] = ip;
+#pragma unroll
+        for (int r = k + 1; r < N; r++)
+        {
+            const bool sw = (ip == r);
+#pragma unroll
+            for (int c = 0; c < N; c++)
+            {
+                const double x = A[k + c * N], y = A[r + c * N];
+                A[k + c * N] = sw ? y : x;
+                A[r + c * N] = sw ? x : y;
+            }
+        }
+        const double d = rcp_nr(A[k + k * N]);
+        A[k + k * N] = 1.0;
+#pragma unroll
+        for (int c = 0; c < N; c++)
+            A[k + c * N] *= d;
+#pragma unroll
+        for (int r = 0; r < N; r++)
+        {
+            if (r == k)
+                continue;
+            const double f = A[r + k * N];
+            A[r + k * N] = 0.0;
+#pragma unroll
+            for (int c = 0; c < N; c++)
+                A[r + c * N] = fma(-f, A[k + c * N], A[r + c * N]);
+        }
+    }
+#pragma unroll
+    for (int k = N - 2; k >= 0; k--)
+    {
+#pragma unroll
+        for (int r = k + 1; r < N; r++)
+        {
+            const bool sw = (piv[k] == r);
+#pragma unroll
+            for (int i = 0; i < N; i++)
+            {
+                const double x = A[i + k * N], y = A[i + r * N];
+                A[i + k * N] = sw ? y : x;
+                A[i + r * N] = sw ? x : y;
+            }
+        }
+    }
+    return singular;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Exact power-of-two pre-scaling for the Jacobi solvers, done entirely on the integer pipe (which is idle in these
 // fp64-bound kernels).  The rotation formulas square differences of squared norms, i.e. they need |a|^4 to be

@@ -137,20 +137,50 @@ struct OpEigSym
 
 // LU<n> / linsolve<Factorization::LU> / MatrixS::I() / det(), include/linalg.hpp:448-533, 933-965,
 // 1176-1187.  HBM-bound like QR.
+#ifndef PPX_LU_PREFETCH
+#define PPX_LU_PREFETCH 1
+#endif
+#ifndef PPX_LU_MINB
+#define PPX_LU_MINB 2
+#endif
 template <int N>
 struct OpLinsolveLU
 {
-    static constexpr int BLOCK = 128, MINB = (N <= 4 ? 4 : 2), MAXW = N * N;
+    static constexpr int BLOCK = 128, MINB = (N >= 6 ? PPX_LU_MINB : 4), MAXW = N * N;
     const double *A;
     const double *b;
     double *x;
     int8_t *status;
+    // the next tile's systems are staged (cp.async) behind the elimination of the current one; the stage holds the
+    // matrices followed by the right-hand sides
+    static constexpr bool PREFETCH = PPX_LU_PREFETCH != 0;
+    static constexpr int IN_WIDTH = N * N + N + 2; // >= both parts in either layout (AoS pads each record to odd)
+    template <class IO>
+    __device__ __forceinline__ void prefetch(const IO &io, double *stage) const
+    {
+        io.template async_load<N * N>(A, stage);
+        io.template async_load<N>(b, stage + IO::stage_doubles(BLOCK, N * N));
+    }
+    template <class IO>
+    __device__ __forceinline__ void compute_store(const IO &io, const double *stage) const
+    {
+        double a[N * N], rhs[N];
+        io.template read_staged<N * N>(stage, a);
+        io.template read_staged<N>(stage + IO::stage_doubles(BLOCK, N * N), rhs);
+        solve_store(io, a, rhs);
+    }
     template <class IO>
     __device__ __forceinline__ void operator()(const IO &io) const
     {
-        double a[N * N], rhs[N], b0[N];
+        double a[N * N], rhs[N];
         io.load(A, a);
         io.load(b, rhs);
+        solve_store(io, a, rhs);
+    }
+    template <class IO>
+    __device__ __forceinline__ void solve_store(const IO &io, double (&a)[N * N], double (&rhs)[N]) const
+    {
+        double b0[N];
 #pragma unroll
         for (int i = 0; i < N; i++)
             b0[i] = rhs[i];
@@ -168,30 +198,52 @@ struct OpLinsolveLU
 template <int N>
 struct OpInverse
 {
-    static constexpr int BLOCK = 128, MINB = (N <= 4 ? 4 : 2), MAXW = N * N;
+#ifndef PPX_INVERSE_PREFETCH
+#define PPX_INVERSE_PREFETCH 1
+#endif
+#ifndef PPX_INVERSE_MINB
+#define PPX_INVERSE_MINB 2
+#endif
+    static constexpr int BLOCK = 128, MINB = (N >= 6 ? PPX_INVERSE_MINB : 4), MAXW = N * N;
     const double *A;
     double *Ai;
+    // 8 N^2 bytes each way and little arithmetic in between: the next tile's matrices are staged (cp.async) behind the
+    // elimination of the current one
+    static constexpr bool PREFETCH = PPX_INVERSE_PREFETCH != 0;
+    static constexpr int IN_WIDTH = N * N;
+    template <class IO>
+    __device__ __forceinline__ void prefetch(const IO &io, double *stage) const
+    {
+        io.template async_load<N * N>(A, stage);
+    }
     template <class IO>
     __device__ __forceinline__ void operator()(const IO &io) const
     {
-        double a[N * N], inv[N * N];
+        double a[N * N];
         io.load(A, a);
+        const bool singular = gauss_jordan_inverse<N>(a);
 #pragma unroll
         for (int i = 0; i < N * N; i++)
-            inv[i] = (i % (N + 1) == 0) ? 1.0 : 0.0;
-        bool even;
-        const bool singular = lu_factor_solve<N, N>(a, inv, even);
+            a[i] = singular ? 0.0 : a[i];
+        io.store(Ai, a);
+    }
+    template <class IO>
+    __device__ __forceinline__ void compute_store(const IO &io, const double *stage) const
+    {
+        double a[N * N];
+        io.template read_staged<N * N>(stage, a);
+        const bool singular = gauss_jordan_inverse<N>(a);
 #pragma unroll
         for (int i = 0; i < N * N; i++)
-            inv[i] = singular ? 0.0 : inv[i]; // MatrixS::I() returns {} on SINGULAR (:938-941)
-        io.store(Ai, inv);
+            a[i] = singular ? 0.0 : a[i]; // MatrixS::I() returns {} on SINGULAR (:938-941)
+        io.store(Ai, a);
     }
 };
 
 template <int N>
 struct OpDet
 {
-    static constexpr int BLOCK = 128, MINB = (N <= 4 ? 4 : 2), MAXW = N * N;
+    static constexpr int BLOCK = 128, MINB = 4, MAXW = N * N;
     const double *A;
     double *det;
     template <class IO>
