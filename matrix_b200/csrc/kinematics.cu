@@ -9,7 +9,26 @@
 #include <cmath>
 
 #include "ppx_launch.cuh"
+
+// ---- configuration of the inverseSpace (CoDo) kernel, needed before ppx_codo.cuh is read ----
+// One CTA of 8 warps per SM, and the warps of the CTA start every trip together (PPX_CODO_ALIGN): the body of a trip is
+// ~60 KB of instructions, twice the SM's instruction cache, so warps that drift apart evict each other's code and the
+// kernel ends up waiting for instruction fetches (2/3 of all cycles in the unaligned first version, profiles/); warps
+// that walk through the code side by side share every fetched line.
+#ifndef PPX_CODO_BLOCK
+#define PPX_CODO_BLOCK 256
+#endif
+#ifndef PPX_CODO_MINB
+#define PPX_CODO_MINB 1
+#endif
+#ifndef PPX_CODO_ALIGN
+#define PPX_CODO_ALIGN 1
+#endif
+
+
+#define PPX_CODO_JSTRIDE PPX_CODO_BLOCK // a lane's Jacobians are interleaved by thread in shared memory
 #include "ppx_codo.cuh"
+constexpr size_t CODO_SMEM = ppx_dev::CODO_LANE_DOUBLES * sizeof(double) * PPX_CODO_BLOCK;
 
 using namespace ppx_dev;
 
@@ -255,27 +274,13 @@ struct IkCodoArgs
     int8_t *status;
 };
 
-// One CTA of 8 warps per SM, and the warps of the CTA start every trip together (PPX_CODO_ALIGN): the body of a trip is
-// ~60 KB of instructions, twice the SM's instruction cache, so warps that drift apart evict each other's code and the
-// kernel ends up waiting for instruction fetches (2/3 of all cycles in the unaligned first version, profiles/); warps
-// that walk through the code side by side share every fetched line.
-#ifndef PPX_CODO_BLOCK
-#define PPX_CODO_BLOCK 256
-#endif
-#ifndef PPX_CODO_MINB
-#define PPX_CODO_MINB 1
-#endif
-#ifndef PPX_CODO_ALIGN
-#define PPX_CODO_ALIGN 1
-#endif
-
 template <int LAYOUT>
 __global__ void __launch_bounds__(PPX_CODO_BLOCK, PPX_CODO_MINB)
     ik_codo_kernel(const __grid_constant__ IkCodoArgs a, size_t n, size_t ld, unsigned long long *next)
 {
     CodoLane st;
-    double jbuf[72];
-    st.jbuf = jbuf;
+    extern __shared__ __align__(16) double codo_smem[];
+    codo_attach(st, LaneArray{codo_smem + threadIdx.x});
     Rigid poseI; // pose^-1
     double q0[6];
     size_t idx = 0;
@@ -362,7 +367,7 @@ int ik_step_n(const double *screws, const double *home, const double *q, const d
 // Launch of a persistent kernel with a work counter: as many CTAs as are resident at once; the counter lives for this
 // launch only (stream-ordered allocation, zeroed on the stream).
 template <class Kernel, class Args>
-int launch_persistent(Kernel kern, int block, const Args &a, size_t n, size_t ld, void *stream)
+int launch_persistent(Kernel kern, int block, size_t smem, const Args &a, size_t n, size_t ld, void *stream)
 {
     DeviceInfo info;
     int device = 0;
@@ -375,11 +380,20 @@ int launch_persistent(Kernel kern, int block, const Args &a, size_t n, size_t ld
     if (e != cudaSuccess)
         return (int)e;
     cudaMemsetAsync(next, 0, sizeof(*next), s);
+    if (smem > 48 * 1024)
+    {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+        {
+            cudaFreeAsync(next, s);
+            return (int)e;
+        }
+    }
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem);
     const size_t want = (n + block - 1) / block;
     const size_t cap = (size_t)info.sms * (per_sm > 0 ? per_sm : 1);
-    kern<<<(unsigned)(want < cap ? want : cap), block, 0, s>>>(a, n, ld, next);
+    kern<<<(unsigned)(want < cap ? want : cap), block, smem, s>>>(a, n, ld, next);
     g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);
     e = cudaPeekAtLastError();
     cudaFreeAsync(next, s);
@@ -453,8 +467,8 @@ int ppx_cuda_batch_ik_solve(const double *screws, const double *home, int njoint
     IkSolveArgs a;
     fold_chain<6>(screws, home, a.ch);
     a.q0 = q0, a.Tt = Ttarget, a.q_out = q_out, a.iters = iters, a.status = status, a.max_iter = max_iter;
-    return layout == PPX_LAYOUT_AOS ? launch_persistent(ik_solve_kernel<LAYOUT_AOS>, 128, a, n, ld, stream)
-                                    : launch_persistent(ik_solve_kernel<LAYOUT_SOA>, 128, a, n, ld, stream);
+    return layout == PPX_LAYOUT_AOS ? launch_persistent(ik_solve_kernel<LAYOUT_AOS>, 128, 0, a, n, ld, stream)
+                                    : launch_persistent(ik_solve_kernel<LAYOUT_SOA>, 128, 0, a, n, ld, stream);
 }
 
 int ppx_cuda_batch_ik_codo(const double *screws, const double *home, int njoints, const double *lo, const double *hi,
@@ -478,8 +492,8 @@ int ppx_cuda_batch_ik_codo(const double *screws, const double *home, int njoints
         a.hi[i] = hi[i];
     }
     a.Tt = Ttarget, a.init = init, a.q_out = q_out, a.x_raw = x_raw, a.fnorm = fnorm, a.status = status;
-    return layout == PPX_LAYOUT_AOS ? launch_persistent(ik_codo_kernel<LAYOUT_AOS>, PPX_CODO_BLOCK, a, n, ld, stream)
-                                    : launch_persistent(ik_codo_kernel<LAYOUT_SOA>, PPX_CODO_BLOCK, a, n, ld, stream);
+    return layout == PPX_LAYOUT_AOS ? launch_persistent(ik_codo_kernel<LAYOUT_AOS>, PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream)
+                                    : launch_persistent(ik_codo_kernel<LAYOUT_SOA>, PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream);
 }
 
 } // extern "C"

@@ -65,7 +65,24 @@ PPX_DEV double codo_sqrt(double a)
     return (hi >= (64 << 20) && hi < (1984 << 20)) ? a * rsqrt_nr(a) : codo_sqrt_ieee(a);
 }
 
-PPX_DEV double codo_dot6(const double (&a)[6], const double (&b)[6])
+// Per-lane arrays that are not worth registers live in shared memory in the kernel, interleaved by thread: element k of
+// this lane is p[k * CODO_JS] with CODO_JS = the CTA size (conflict-free; and unlike the stack it cannot be evicted to
+// L2 / DRAM: the first version of this kernel moved 10x its algorithmic bytes through DRAM as local-memory traffic).
+// These are the two Jacobians (indexed by the running joint of the rolled chain loop) and the vectors the optimiser
+// carries from one evaluation to the next but does not touch during it.  The host build uses CODO_JS = 1.
+#ifndef PPX_CODO_JSTRIDE
+#define PPX_CODO_JSTRIDE 1
+#endif
+constexpr int CODO_JS = PPX_CODO_JSTRIDE;
+struct LaneArray
+{
+    double *p;
+    PPX_DEV double &operator[](int k) const { return p[(size_t)k * CODO_JS]; }
+    PPX_DEV LaneArray from(int k) const { return LaneArray{p + (size_t)k * CODO_JS}; }
+};
+
+template <class A, class B>
+PPX_DEV double codo_dot6(const A &a, const B &b)
 {
     double r = 0.0;
 #pragma unroll
@@ -73,8 +90,13 @@ PPX_DEV double codo_dot6(const double (&a)[6], const double (&b)[6])
         r = fma(a[i], b[i], r);
     return r;
 }
-PPX_DEV double codo_norm6(const double (&v)[6]) { return codo_sqrt_fast(codo_dot6(v, v)); }
-PPX_DEV double codo_min6(const double (&v)[6])
+template <class A>
+PPX_DEV double codo_norm6(const A &v)
+{
+    return codo_sqrt_fast(codo_dot6(v, v));
+}
+template <class A>
+PPX_DEV double codo_min6(const A &v)
 {
     double m = v[0];
 #pragma unroll
@@ -83,7 +105,8 @@ PPX_DEV double codo_min6(const double (&v)[6])
     return m;
 }
 // y = J x, J column-major 6 x 6
-PPX_DEV void codo_matvec(const double *J, const double (&x)[6], double (&y)[6])
+template <class X>
+PPX_DEV void codo_matvec(const LaneArray J, const X &x, double (&y)[6])
 {
 #pragma unroll
     for (int i = 0; i < 6; i++)
@@ -101,7 +124,7 @@ PPX_DEV void codo_matvec(const double *J, const double (&x)[6], double (&y)[6])
 // The prefix P starts as the identity, for which Ad(P) S and P E are exact, so the rolled loop produces the bits of
 // the unrolled poe_fk_jacobian.
 template <int NJ>
-PPX_DEV void codo_eval(const ChainConst<NJ> &ch, const Rigid &poseI, const double *q, double (&fx)[6], double *jac)
+PPX_DEV void codo_eval(const ChainConst<NJ> &ch, const Rigid &poseI, const double *q, double (&fx)[6], const LaneArray jac)
 {
     Rigid P;
     rigid_identity(P);
@@ -152,20 +175,26 @@ enum CodoPhase
 struct CodoLane
 {
     double x[6], fx[6];  // iterate and residual there
-    double *jbuf;        // -> 2 x 36 doubles owned by the caller (kept apart so that the rest of the state can live in
-                         // registers): the Jacobian at x is jbuf[36 cur ..], the evaluation at `probe` writes the other
-    int cur;             // half, and accepting a trial point is a flip of `cur`
+    LaneArray jbuf;      // 2 x 36 doubles owned by the caller: the Jacobian at x is jbuf[36 cur ..], the evaluation at
+    int cur;             // `probe` writes the other half, and accepting a trial point is a flip of `cur`
     double probe[6];             // where the next evaluation happens
-    double grad[6], p[6];        // carried from trip to trip (Barzilai-Borwein lambda, :574-583)
-    double pc[6], pn[6], dgrad[6], G[6]; // of the running trip; needed again every time the trust region shrinks
+    LaneArray grad, p;           // carried from trip to trip (Barzilai-Borwein lambda, :574-583)
+    LaneArray pn, dgrad, G;      // of the running trip; needed again every time the trust region shrinks
     double fnrm, fnrm_old, delta0, delta1, vert, nGdgrad, y;
     unsigned itc;
     int stat, phase;
     bool singular;
 };
 
-PPX_DEV const double *codo_jac(const CodoLane &s) { return s.jbuf + 36 * s.cur; }
-PPX_DEV double *codo_jac_probe(CodoLane &s) { return s.jbuf + 36 * (s.cur ^ 1); }
+// hands the lane its CODO_LANE_DOUBLES doubles of interleaved storage
+constexpr int CODO_LANE_DOUBLES = 72 + 5 * 6;
+PPX_DEV void codo_attach(CodoLane &s, LaneArray mem)
+{
+    s.jbuf = mem;
+    s.grad = mem.from(72), s.p = mem.from(78), s.pn = mem.from(84), s.dgrad = mem.from(90), s.G = mem.from(96);
+}
+PPX_DEV LaneArray codo_jac(const CodoLane &s) { return s.jbuf.from(36 * s.cur); }
+PPX_DEV LaneArray codo_jac_probe(const CodoLane &s) { return s.jbuf.from(36 * (s.cur ^ 1)); }
 
 // after x was set: false -> evaluate at probe; true -> finished (illegal start, :546-556)
 PPX_DEV bool codo_begin(const double (&lo)[6], const double (&hi)[6], CodoLane &s)
@@ -287,7 +316,7 @@ PPX_DEV unsigned codo_trip_head(const double (&lo)[6], const double (&hi)[6], Co
     constexpr unsigned ITMAX = 300;
     double(&x)[6] = s.x;
     double(&fx)[6] = s.fx;
-    const double *jac = codo_jac(s);
+    const LaneArray jac = codo_jac(s);
     {
         if (!(s.fnrm > FTOLA && s.itc++ < ITMAX))
         {
@@ -355,9 +384,6 @@ PPX_DEV unsigned codo_trip_head(const double (&lo)[6], const double (&hi)[6], Co
         codo_matvec(jac, s.dgrad, jd);
         const double ratio = codo_div(codo_norm6(tmp), codo_norm6(jd));
         s.vert = ratio * ratio;
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-            s.pc[i] = -s.vert * s.dgrad[i];
         if (s.itc == 1)
         {
 #pragma unroll
@@ -402,14 +428,14 @@ PPX_DEV void codo_build(const double (&lo)[6], const double (&hi)[6], CodoLane &
     constexpr double MAX_SP = CODO_MAX_SP, theta = 0.99995;
     double(&x)[6] = s.x;
     double(&fx)[6] = s.fx;
-    const double *jac = codo_jac(s);
+    const LaneArray jac = codo_jac(s);
     {
         double pciv[6], alp[6];
         const bool cauchy = s.vert * s.nGdgrad > s.delta1;
         const double shrink = -codo_div(s.delta1, s.nGdgrad);
 #pragma unroll
         for (int i = 0; i < 6; i++)
-            pciv[i] = cauchy ? shrink * s.dgrad[i] : s.pc[i];
+            pciv[i] = cauchy ? shrink * s.dgrad[i] : -s.vert * s.dgrad[i]; // else the Cauchy point pc
 #pragma unroll
         for (int i = 0; i < 6; i++)
         {

@@ -58,8 +58,8 @@ extern "C" int codo_host_run(const double *screws, const double *home, const dou
     for (size_t idx = 0; idx < n; idx++)
     {
         CodoLane st;
-        double jbuf[72];
-        st.jbuf = jbuf;
+        double mem[CODO_LANE_DOUBLES];
+        codo_attach(st, LaneArray{mem});
         double m[16], q0[6];
         std::memcpy(m, Tt + 16 * idx, sizeof(m));
         for (int k = 0; k < 6; k++)
