@@ -745,3 +745,98 @@ def test_full_size_32M_ik_newton_step(mb):
     good = e1 < 10 * e0 * e0 + 1e-12  # quadratic contraction
     assert float(good.double().mean()) > 0.97  # the rest sits near UR5 singularities
     assert float(e1.median()) < 0.05 * float(e0.median())
+
+
+# --------------------------------------------------------------------------------------- out-of-bounds canaries
+@pytest.mark.parametrize("n", [1, 31, 33, 255, 257, 1000])
+def test_persistent_and_staged_kernels_stay_inside_their_buffers(mb, port, n):
+    """The persistent kernels (ik_solve, ik_codo: instances claimed from a counter) and the cp.async-staged ones
+    (inverse, linsolve<LU>) called through the raw C ABI on buffers embedded in canary-filled allocations, ragged n,
+    both layouts: every output byte outside [0, n) keeps its canary, and the inside matches the oracle."""
+    import ctypes as C
+    from matrix_b200 import _lib
+    lib, CAN = _lib.lib, -7.25
+    S, M = synth.UR5_SCREWS, synth.UR5_HOME
+    Sp = np.ascontiguousarray(S, dtype=np.float64)
+    Mp = np.ascontiguousarray(M, dtype=np.float64)
+    lo, hi = -np.pi * np.ones(6), np.pi * np.ones(6)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    q = synth.joint_angles(n, seed=0xD1) * 0.9
+    Tt = port.poe_fk_jacobian(S, M, q + synth.ik_offsets(n), want_Js=False)[0]
+    A = synth.dense(n, 6, 6, seed=0xD2)
+    b = synth.dense(n, 6, 1, seed=0xD3)
+    ref_codo = port.ik_codo(S, M, lo, hi, Tt, q)
+    ref_newton = port.ik_solve(S, M, q, Tt, 20)
+    ref_inv, (ref_x, _) = port.inverse(6, A), port.linsolve_lu(6, A, b)
+    pad = 96
+    for layout in (mb.AOS, mb.SOA):
+        ld = n + 37 if layout == mb.SOA else n
+
+        def put(a):  # device copy of the records in `layout`, leading dimension ld
+            t = dev(a)
+            if layout == mb.AOS:
+                return t.contiguous()
+            out = torch.zeros((a.shape[1], ld), dtype=torch.float64, device="cuda")
+            out[:, :n] = t.t()
+            return out
+
+        def canary(width):  # (whole allocation, pointer to the embedded output)
+            whole = torch.full((pad + width * ld + pad,), CAN, dtype=torch.float64, device="cuda")
+            return whole, C.c_void_p(whole.data_ptr() + 8 * pad)
+
+        def inside(whole, width):  # -> records [n, width]; asserts that everything else is still canary
+            body = whole[pad:pad + width * ld]
+            assert torch.all(whole[:pad] == CAN) and torch.all(whole[pad + width * ld:] == CAN)
+            if layout == mb.AOS:
+                return body.view(n, width).cpu().numpy()
+            body = body.view(width, ld)
+            assert torch.all(body[:, n:] == CAN)
+            return body[:, :n].t().cpu().numpy()
+
+        dq, dT, dA, db = put(q), put(Tt), put(A), put(b)
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        ist = torch.full((n + 2 * pad,), -3, dtype=torch.int8, device="cuda")
+        iit = torch.full((n + 2 * pad,), -3, dtype=torch.int32, device="cuda")
+        ifn = torch.full((n + 2 * pad,), CAN, dtype=torch.float64, device="cuda")
+        # inverseSpace (CoDo)
+        wq, pq = canary(6)
+        wx, px = canary(6)
+        _lib.check(lib.ppx_cuda_batch_ik_codo(vp(Sp), vp(Mp), 6, vp(lo), vp(hi), p(dT), p(dq), pq, px,
+                                              C.c_void_p(ifn.data_ptr() + 8 * pad), C.c_void_p(ist.data_ptr() + pad),
+                                              n, layout, ld, None))
+        torch.cuda.synchronize()
+        qs, st = inside(wq, 6), ist[pad:pad + n].cpu().numpy()
+        inside(wx, 6)
+        assert torch.all(ist[:pad] == -3) and torch.all(ist[pad + n:] == -3)
+        assert torch.all(ifn[:pad] == CAN) and torch.all(ifn[pad + n:] == CAN)
+        fn = ifn[pad:pad + n].cpu().numpy()
+        both = (st == mb.CONVERGED) & (ref_codo[3] == mb.CONVERGED) & (fn < 5e-8) & (ref_codo[2] < 5e-8)
+        assert (st == ref_codo[3]).mean() >= 0.99 and both.sum() >= 0.9 * n - 1
+        assert np.abs(port.poe_fk_jacobian(S, M, qs[both], want_Js=False)[0] - Tt[both]).max() < 5e-7
+        # Newton loop
+        ist.fill_(-3)
+        wq, pq = canary(6)
+        _lib.check(lib.ppx_cuda_batch_ik_solve(vp(Sp), vp(Mp), 6, p(dq), p(dT), 20, pq,
+                                               C.c_void_p(iit.data_ptr() + 4 * pad), C.c_void_p(ist.data_ptr() + pad),
+                                               n, layout, ld, None))
+        torch.cuda.synchronize()
+        qs = inside(wq, 6)
+        assert torch.all(iit[:pad] == -3) and torch.all(iit[pad + n:] == -3)
+        assert torch.all(ist[:pad] == -3) and torch.all(ist[pad + n:] == -3)
+        it = iit[pad:pad + n].cpu().numpy()
+        assert np.all((it >= 1) & (it <= 20)) and (it == ref_newton[1]).mean() >= 0.9
+        conv = (ist[pad:pad + n].cpu().numpy() == mb.CONVERGED)
+        assert conv.sum() >= 0.9 * n - 1
+        assert np.abs(port.poe_fk_jacobian(S, M, qs[conv], want_Js=False)[0] - Tt[conv]).max() < 1.2e-7
+        # inverse, linsolve<LU>
+        wi, pi = canary(36)
+        _lib.check(lib.ppx_cuda_batch_inverse(6, p(dA), pi, n, layout, ld, None))
+        wl, pl = canary(6)
+        ist.fill_(-3)
+        _lib.check(lib.ppx_cuda_batch_linsolve_lu(6, p(dA), p(db), pl, C.c_void_p(ist.data_ptr() + pad), n, layout, ld,
+                                                  None))
+        torch.cuda.synchronize()
+        kappa = np.linalg.cond(A.reshape(n, 6, 6).transpose(0, 2, 1))
+        assert np.all(rel_err(inside(wi, 36), ref_inv) <= REL * np.maximum(1.0, kappa))
+        assert np.all(rel_err(inside(wl, 6), ref_x) <= REL * np.maximum(1.0, kappa))
+        assert torch.all(ist[:pad] == -3) and torch.all(ist[pad + n:] == -3) and torch.all(ist[pad:pad + n] == 0)
