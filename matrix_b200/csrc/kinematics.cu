@@ -11,10 +11,10 @@
 #include "ppx_launch.cuh"
 
 // ---- configuration of the inverseSpace (CoDo) kernel, needed before ppx_codo.cuh is read ----
-// One CTA of 8 warps per SM, and the warps of the CTA start every trip together (PPX_CODO_ALIGN): the body of a trip is
-// ~60 KB of instructions, twice the SM's instruction cache, so warps that drift apart evict each other's code and the
-// kernel ends up waiting for instruction fetches (2/3 of all cycles in the unaligned first version, profiles/); warps
-// that walk through the code side by side share every fetched line.
+// One CTA of 8 warps per SM (232 registers and 816 B of shared memory per lane).  PPX_CODO_ALIGN = 1 makes the warps of
+// the CTA start every trip together (the loop's exit test becomes a __syncthreads_or): that paid (+4 %) while the body
+// of a trip was far larger than the SM's instruction cache and the kernel waited for instruction fetches; with the
+// present footprint the barrier costs more than it saves (-2 %), so it is off.
 #ifndef PPX_CODO_BLOCK
 #define PPX_CODO_BLOCK 256
 #endif
@@ -22,7 +22,7 @@
 #define PPX_CODO_MINB 1
 #endif
 #ifndef PPX_CODO_ALIGN
-#define PPX_CODO_ALIGN 1
+#define PPX_CODO_ALIGN 0
 #endif
 
 
