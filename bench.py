@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--layout", choices=["soa", "aos"], default="soa", help="record layout of --all-ops")
     ap.add_argument("--all-ops", action="store_true",
                     help="time every batched entry point (kernel only, SoA) next to its CPU reference; one JSON line")
     args = ap.parse_args()
@@ -250,7 +251,9 @@ def main():
         from bench_cpu import NTHREADS, cpu_op, load_cpu_oracle
         oracle, kind = load_cpu_oracle()
         rows = []
-        for op in ops_table.make_ops():
+        from matrix_b200 import batch as _mb
+        op_layout = _mb.AOS if args.layout == "aos" else _mb.SOA
+        for op in ops_table.make_ops(op_layout):
             op.setup(device)
             for _ in range(3):
                 op.step()
@@ -277,7 +280,8 @@ def main():
                          "cpu_kind": kind})
             op.step = None
             torch.cuda.empty_cache()
-        print(json.dumps({"all_ops": rows, "hbm_peak_gbs": hbm_peak, "layout": "soa (device resident)", "dtype": "f64"}))
+        print(json.dumps({"all_ops": rows, "hbm_peak_gbs": hbm_peak, "layout": f"{args.layout} (device resident)",
+                          "dtype": "f64"}))
         return
     cls = WORKLOADS[args.workload]
     n = args.n or cls.n_default

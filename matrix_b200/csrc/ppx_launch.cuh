@@ -93,24 +93,39 @@ struct has_prefetch<Op, typename std::enable_if<Op::PREFETCH>::type> : std::true
 {
 };
 
+// an op may ask for the staged kernel on the record (AoS) layout only: PREFETCH_AOS_ONLY = true
+template <class Op, class = void>
+struct prefetch_aos_only : std::false_type
+{
+};
+template <class Op>
+struct prefetch_aos_only<Op, typename std::enable_if<Op::PREFETCH_AOS_ONLY>::type> : std::true_type
+{
+};
 template <int LAYOUT, class Op>
-constexpr typename std::enable_if<has_prefetch<Op>::value, size_t>::type stage_bytes()
+struct use_prefetch
+    : std::integral_constant<bool, has_prefetch<Op>::value && !(prefetch_aos_only<Op>::value && LAYOUT == LAYOUT_SOA)>
+{
+};
+
+template <int LAYOUT, class Op>
+constexpr typename std::enable_if<use_prefetch<LAYOUT, Op>::value, size_t>::type stage_bytes()
 {
     return 2 * TileIO<LAYOUT>::stage_doubles(Op::BLOCK, Op::IN_WIDTH) * sizeof(double);
 }
 template <int LAYOUT, class Op>
-constexpr typename std::enable_if<!has_prefetch<Op>::value, size_t>::type stage_bytes()
+constexpr typename std::enable_if<!use_prefetch<LAYOUT, Op>::value, size_t>::type stage_bytes()
 {
     return 0;
 }
 
 template <int LAYOUT, class Op>
-typename std::enable_if<has_prefetch<Op>::value, void (*)(const Op, size_t, size_t)>::type pick_kernel()
+typename std::enable_if<use_prefetch<LAYOUT, Op>::value, void (*)(const Op, size_t, size_t)>::type pick_kernel()
 {
     return batch_kernel_pf<LAYOUT, Op>;
 }
 template <int LAYOUT, class Op>
-typename std::enable_if<!has_prefetch<Op>::value, void (*)(const Op, size_t, size_t)>::type pick_kernel()
+typename std::enable_if<!use_prefetch<LAYOUT, Op>::value, void (*)(const Op, size_t, size_t)>::type pick_kernel()
 {
     return batch_kernel<LAYOUT, Op>;
 }

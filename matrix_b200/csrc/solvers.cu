@@ -246,11 +246,34 @@ struct OpDet
     static constexpr int BLOCK = 128, MINB = 4, MAXW = N * N;
     const double *A;
     double *det;
+    // Read-dominated (8 N^2 bytes in, 8 out).  On component planes the plain kernel already runs at the HBM peak and
+    // staging costs 20 %; on records, where the loads go through the warp's shared-memory tile anyway, staging the
+    // next tile with cp.async gains 12 %.
+    static constexpr bool PREFETCH = true, PREFETCH_AOS_ONLY = true;
+    static constexpr int IN_WIDTH = N * N;
+    template <class IO>
+    __device__ __forceinline__ void prefetch(const IO &io, double *stage) const
+    {
+        io.template async_load<N * N>(A, stage);
+    }
+    template <class IO>
+    __device__ __forceinline__ void compute_store(const IO &io, const double *stage) const
+    {
+        double a[N * N];
+        io.template read_staged<N * N>(stage, a);
+        factor_store(io, a);
+    }
     template <class IO>
     __device__ __forceinline__ void operator()(const IO &io) const
     {
-        double a[N * N], dummy[N];
+        double a[N * N];
         io.load(A, a);
+        factor_store(io, a);
+    }
+    template <class IO>
+    __device__ __forceinline__ void factor_store(const IO &io, double (&a)[N * N]) const
+    {
+        double dummy[N];
         bool even;
         const bool singular = lu_factor_solve<N, 0>(a, dummy, even);
         double D = even ? 1.0 : -1.0; // :959-964

@@ -55,17 +55,26 @@ def _lie(n, dev):
     return xi, T, T2, w, R
 
 
-def make_ops():
+def make_ops(layout=mb.SOA):
+    """layout = mb.SOA (component planes, the fast layout) or mb.AOS (arrays of the reference's dense records)"""
     S, M = synth.UR5_SCREWS, synth.UR5_HOME
     ops = []
+    aos = layout == mb.AOS
+
+    def lay(t):  # an SoA tensor [width, n] in the requested layout
+        return mb.to_aos(t) if aos else t
+
+    def out(w, cnt, dev):
+        return torch.empty((cnt, w) if aos else (w, cnt), dtype=torch.float64, device=dev)
 
     def lie_op(name, pick, fn, win, wout, ref):
         def setup(n, dev):
             xi, T, T2, w, R = _lie(n, dev)
-            x = {"xi": xi, "T": T, "w": w, "R": R}[pick]
-            out = torch.empty((wout, n), dtype=torch.float64, device=dev)
-            return lambda: fn(x, layout=mb.SOA, out=out)
-        ops.append(Op(name, 1 << 24, 8 * (win + wout), setup, ref, 8 * ((12 if pick == "T" else win) + wout)))
+            x = lay({"xi": xi, "T": T, "w": w, "R": R}[pick])
+            o = out(wout, n, dev)
+            return lambda: fn(x, layout=layout, out=o)
+        ops.append(Op(name, 1 << 24, 8 * (win + wout), setup, ref,
+                      8 * ((12 if pick == "T" and not aos else win) + wout)))
 
     lie_op("so3_exp", "w", mb.so3_exp, 3, 9, "liegroup.hpp:116-133")
     lie_op("SO3_log", "R", mb.SO3_log, 9, 3, "liegroup.hpp:60-92")
@@ -77,31 +86,31 @@ def make_ops():
 
     def setup_mul(n, dev):
         xi, T, T2, w, R = _lie(n, dev)
-        out = torch.empty_like(T)
-        return lambda: mb.SE3_mul(T, T2, layout=mb.SOA, out=out)
-    ops.append(Op("SE3_mul", 1 << 24, 8 * 48, setup_mul, "liegroup.hpp:204-207", 8 * 40))
+        T, T2 = lay(T), lay(T2)
+        o = torch.empty_like(T)
+        return lambda: mb.SE3_mul(T, T2, layout=layout, out=o)
+    ops.append(Op("SE3_mul", 1 << 24, 8 * 48, setup_mul, "liegroup.hpp:204-207", 8 * (48 if aos else 40)))
 
     def setup_jac(n, dev):
-        w = _lie(n, dev)[3]
-        out = torch.empty((9, n), dtype=torch.float64, device=dev)
-        return lambda: mb.so3_jac("ljacinv", w, layout=mb.SOA, out=out)
+        w = lay(_lie(n, dev)[3])
+        o = out(9, n, dev)
+        return lambda: mb.so3_jac("ljacinv", w, layout=layout, out=o)
     ops.append(Op("so3_ljacinv", 1 << 24, 8 * 12, setup_jac, "liegroup.hpp:157-170"))
-
-    def out(w, cnt, dev):
-        return torch.empty((w, cnt), dtype=torch.float64, device=dev)
 
     def dense_op(name, m, n_, count, seed, bytes_, ref, launch, out_widths, with_status=False):
         """launch(A, b, outs, status, count) issues the C-ABI call; outs are SoA tensors of the given widths"""
         def setup(cnt, dev):
-            A = mb.to_soa(_rec(cnt, m * n_, seed, -1.0, 1.0, dev))
-            b = mb.to_soa(_rec(cnt, m, seed + 1, -1.0, 1.0, dev))
+            A = _rec(cnt, m * n_, seed, -1.0, 1.0, dev)
+            b = _rec(cnt, m, seed + 1, -1.0, 1.0, dev)
+            if not aos:
+                A, b = mb.to_soa(A), mb.to_soa(b)
             outs = [out(w, cnt, dev) for w in out_widths]
             status = torch.empty(cnt, dtype=torch.int8, device=dev) if with_status else None
             return lambda: check(launch(A, b, outs, status, cnt))
         ops.append(Op(name, count, bytes_, setup, ref))
 
     def tail(c):
-        return (c, mb.SOA, c, mb._stream())
+        return (c, layout, c, mb._stream())
 
     dense_op("linsolve_svd_6x6", 6, 6, 1 << 23, 0x201, 8 * (36 + 6 + 6), "linalg.hpp:886-913, 1202-1209",
              lambda A, b, o, s, c: lib.ppx_cuda_batch_linsolve_svd(6, 6, _p(A), _p(b), _p(o[0]), *tail(c)), [6])
@@ -123,8 +132,8 @@ def make_ops():
         kin = mb.Kinematics(S, M)
         q = _rec(n, 6, synth.SEEDS["ik_newton_step"], -np.pi, np.pi, dev)
         d = _rec(n, 6, synth.SEEDS["ik_newton_step"] ^ 0xA5A5, -0.05, 0.05, dev)
-        Tt = kin.forwardSpace(mb.to_soa(q + d), layout=mb.SOA)
-        q = mb.to_soa(q)
-        return lambda: kin.inverseSpaceNewton(Tt, q, 20, layout=mb.SOA)
+        Tt = lay(kin.forwardSpace(mb.to_soa(q + d), layout=mb.SOA))
+        q = q if aos else mb.to_soa(q)
+        return lambda: kin.inverseSpaceNewton(Tt, q, 20, layout=layout)
     ops.append(Op("ik_solve_newton_loop", 1 << 22, 8 * (6 + 16 + 6) + 5, setup_iksolve, "test/lie_test.cpp:96-113"))
     return ops

@@ -9,9 +9,16 @@ import torch
 sys.path.insert(0, ".")
 from matrix_b200 import ops_table  # noqa: E402
 
+from matrix_b200 import batch as mb  # noqa: E402
+
 dev = torch.device("cuda", 0)
-want = set(sys.argv[1:])
-for op in ops_table.make_ops():
+argv = sys.argv[1:]
+layout = mb.SOA
+if argv and argv[0] in ("--aos", "--soa"):
+    layout = mb.AOS if argv[0] == "--aos" else mb.SOA
+    argv = argv[1:]
+want = set(argv)
+for op in ops_table.make_ops(layout):
     if want and op.name not in want:
         continue
     op.setup(dev)
