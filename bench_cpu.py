@@ -206,5 +206,6 @@ CPU = {
     "svd_6x6": cpu_svd_6x6,
     "eig_sym_4": cpu_eig_sym_4,
     "ik_newton_step": cpu_ik_newton_step,
+    "ik_newton_step_svd": cpu_ik_newton_step,
     "inverse_space_codo": cpu_inverse_space_codo,
 }

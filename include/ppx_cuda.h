@@ -68,6 +68,12 @@ int ppx_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
 int ppx_cuda_stream_synchronize(void *stream);
 /* number of kernel launches this library has issued in this process (all threads) */
 uint64_t ppx_cuda_launch_count(void);
+/* Square linsolve<SVD> systems (ppx_cuda_batch_linsolve_svd with m == n, the Newton step of ik_newton_step / ik_solve)
+ * are solved by LU with partial pivoting whenever every pivot is above 1e-8 of the largest -- the same A^+ b to the same
+ * accuracy, the truncation of SVD::solve (linalg.hpp:889-901) only acts beyond cond ~ 2e15 -- and by the Jacobi SVD
+ * otherwise.  enable = 0 forces the Jacobi SVD solve everywhere (to measure it); returns the previous setting.
+ * Process-wide, read at launch time. */
+int ppx_cuda_set_square_solve_lu(int enable);
 
 /* records of `width` doubles: dense AoS (n*width) <-> component-major SoA (width*ld) */
 int ppx_cuda_aos_to_soa(const double *aos, double *soa, int width, size_t n, size_t ld, void *stream);

@@ -93,6 +93,7 @@ _RESTYPES = {
     "ppx_cuda_version": (C.c_char_p, []),
     "ppx_cuda_error_string": (C.c_char_p, [_i]),
     "ppx_cuda_launch_count": (C.c_uint64, []),
+    "ppx_cuda_set_square_solve_lu": (C.c_int, [_i]),
 }
 
 EXPORTS = sorted(list(_SIGNATURES) + list(_RESTYPES))
@@ -118,3 +119,8 @@ def version():
 
 def launch_count():
     return int(lib.ppx_cuda_launch_count())
+
+
+def set_square_solve_lu(enable):
+    """LU fast path of square linsolve<SVD> / the IK Newton step on (default) or off; -> previous setting"""
+    return bool(lib.ppx_cuda_set_square_solve_lu(1 if enable else 0))

@@ -76,16 +76,18 @@ struct OpFkJacobian
     }
 };
 
-// dq = linsolve<SVD>(Js, Vs).x: a square Jacobian (6 joints) takes the row-orthogonalising solve that needs no V
+// dq = linsolve<SVD>(Js, Vs).x: a square Jacobian (6 joints) needs no V, and no SVD either unless it is close to
+// singular (square_pinv_solve)
 template <int NJ>
 __device__ __forceinline__ typename std::enable_if<NJ == 6>::type svd_solve_dispatch(double (&js)[36], const double (&vs)[6],
-                                                                                    double (&dq)[6])
+                                                                                    double (&dq)[6], bool allow_lu)
 {
-    jacobi_rowsolve<6>(js, vs, dq);
+    square_pinv_solve<6>(js, vs, dq, allow_lu);
 }
 template <int NJ>
 __device__ __forceinline__ typename std::enable_if<NJ != 6>::type svd_solve_dispatch(double (&js)[6 * NJ],
-                                                                                    const double (&vs)[6], double (&dq)[NJ])
+                                                                                    const double (&vs)[6], double (&dq)[NJ],
+                                                                                    bool)
 {
     double V[NJ * NJ], w2[NJ];
     jacobi_svd_core<6, NJ, true>(js, V, w2);
@@ -95,7 +97,7 @@ __device__ __forceinline__ typename std::enable_if<NJ != 6>::type svd_solve_disp
 // Vs = Ad(T(q)) log(T(q)^-1 Tt),  dq = pinv(Js(q)) Vs  (test/lie_test.cpp:104-110)
 template <int NJ>
 __device__ __forceinline__ void ik_newton_update(const ChainConst<NJ> &ch, const Rigid &target, double (&q)[NJ],
-                                                 double (&vs)[6])
+                                                 double (&vs)[6], bool allow_lu)
 {
     Rigid t, ti, x;
     double js[6 * NJ];
@@ -111,7 +113,7 @@ __device__ __forceinline__ void ik_newton_update(const ChainConst<NJ> &ch, const
     const double lw[3] = {lg[0], lg[1], lg[2]}, lv[3] = {lg[3], lg[4], lg[5]};
     rigid_adjoint_apply(t, lw, lv, vs);
     double dq[NJ];
-    svd_solve_dispatch<NJ>(js, vs, dq);
+    svd_solve_dispatch<NJ>(js, vs, dq, allow_lu);
 #pragma unroll
     for (int i = 0; i < NJ; i++)
         q[i] += dq[i];
@@ -127,6 +129,7 @@ struct OpIkStep
     const double *Tt;
     double *q_out;
     double *Vs;
+    bool allow_lu;
     template <class IO>
     __device__ __forceinline__ void operator()(const IO &io) const
     {
@@ -135,7 +138,7 @@ struct OpIkStep
         io.load(q, qi);
         io.load(Tt, m);
         rigid_from_record(m, target);
-        ik_newton_update<NJ>(ch, target, qi, vs);
+        ik_newton_update<NJ>(ch, target, qi, vs, allow_lu);
         io.store(q_out, qi);
         if (Vs != nullptr)
             io.store(Vs, vs);
@@ -188,6 +191,7 @@ struct IkSolveArgs
     int32_t *iters;
     int8_t *status;
     int max_iter;
+    bool allow_lu;
 };
 
 template <int LAYOUT>
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(128, 1)
 #pragma unroll
         for (int i = 0; i < NJ; i++)
             qn[i] = qi[i];
-        ik_newton_update<NJ>(a.ch, target, qn, vs);
+        ik_newton_update<NJ>(a.ch, target, qn, vs, a.allow_lu);
         if (busy && !finished)
         {
 #pragma unroll
@@ -361,7 +365,7 @@ int ik_step_n(const double *screws, const double *home, const double *q, const d
 {
     ChainConst<NJ> ch;
     fold_chain<NJ>(screws, home, ch);
-    return dispatch(layout, OpIkStep<NJ>{ch, q, Tt, q_out, Vs}, n, ld, stream);
+    return dispatch(layout, OpIkStep<NJ>{ch, q, Tt, q_out, Vs, g_ppx_square_lu.load(std::memory_order_relaxed) != 0}, n, ld, stream);
 }
 
 // Launch of a persistent kernel with a work counter: as many CTAs as are resident at once; the counter lives for this
@@ -467,6 +471,7 @@ int ppx_cuda_batch_ik_solve(const double *screws, const double *home, int njoint
     IkSolveArgs a;
     fold_chain<6>(screws, home, a.ch);
     a.q0 = q0, a.Tt = Ttarget, a.q_out = q_out, a.iters = iters, a.status = status, a.max_iter = max_iter;
+    a.allow_lu = g_ppx_square_lu.load(std::memory_order_relaxed) != 0;
     return layout == PPX_LAYOUT_AOS ? launch_persistent(ik_solve_kernel<LAYOUT_AOS>, 128, 0, a, n, ld, stream)
                                     : launch_persistent(ik_solve_kernel<LAYOUT_SOA>, 128, 0, a, n, ld, stream);
 }

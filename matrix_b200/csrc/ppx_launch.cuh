@@ -16,6 +16,7 @@
 #include "ppx_math.cuh"
 
 extern std::atomic<uint64_t> g_ppx_launch_count; // util.cu
+extern std::atomic<int> g_ppx_square_lu;         // util.cu: ppx_cuda_set_square_solve_lu
 
 #define PPX_CHECK_PTRS(...)                          \
     do                                               \

@@ -1081,6 +1081,47 @@ PPX_DEV void jacobi_rowsolve(const double (&A)[N * N], const double (&b)[N], dou
     }
 }
 
+// linsolve<Factorization::SVD> on a SQUARE system (SVD::solve, linalg.hpp:886-913) = A^+ b with singular values below
+// 0.5 sqrt(2n+1) w_max EPS_DP dropped.  That truncation can only act when cond(A) > ~2e15; everywhere else A^+ b is
+// A^-1 b, and a backward-stable solver returns it to the same accuracy (~cond eps) whatever the factorisation.  So the
+// system is first solved by LU with partial pivoting (~1/30 of the arithmetic of the Jacobi solve); if any pivot falls
+// below 1e-8 of the largest one -- seven orders of magnitude before truncation could matter, also catching zero, inf and
+// NaN pivots -- the row-orthogonalising Jacobi solve is run as well and its result taken for those lanes.  The decision
+// to run it is per warp, so well-conditioned batches never execute it.  `allow_lu = false` forces the Jacobi path.
+template <int N>
+PPX_DEV void square_pinv_solve(const double (&A)[N * N], const double (&b)[N], double (&x)[N], bool allow_lu)
+{
+    double lu[N * N], rx[N];
+#pragma unroll
+    for (int i = 0; i < N * N; i++)
+        lu[i] = A[i];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        rx[i] = b[i];
+    bool even;
+    lu_factor_solve<N, 1>(lu, rx, even);
+    double pmax = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k++)
+        pmax = fmax(pmax, fabs(lu[k + k * N]));
+    bool easy = allow_lu;
+#pragma unroll
+    for (int k = 0; k < N; k++)
+        easy = easy && fabs(lu[k + k * N]) > 1e-8 * pmax;
+    if (__all_sync(0xffffffffu, easy))
+    {
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            x[i] = rx[i];
+        return;
+    }
+    double xs[N];
+    jacobi_rowsolve<N>(A, b, xs);
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        x[i] = easy ? rx[i] : xs[i];
+}
+
 // Cyclic Jacobi eigensolver for a symmetric N x N matrix (EigenValue<n>, include/linalg.hpp:967-1167:
 // same result as tred2 + implicit QL up to rounding and eigenvector sign).  S is read through its
 // lower triangle like the reference's tred2 (z(i,k), k <= i).  d = eigenvalues, Z = eigenvectors in

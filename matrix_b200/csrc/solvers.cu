@@ -77,17 +77,18 @@ struct OpSVD
     }
 };
 
-// square systems: row-orthogonalising solve (no V); rectangular ones: column Jacobi with V
+// square systems: LU, or the row-orthogonalising Jacobi solve (no V) when close to singular (square_pinv_solve);
+// rectangular ones: column Jacobi with V
 template <int N>
 __device__ __forceinline__ void solve_scaled(double (&a)[N * N], double (&)[N * N], double (&)[N], const double (&rhs)[N],
-                                             double (&sol)[N])
+                                             double (&sol)[N], bool allow_lu)
 {
-    jacobi_rowsolve<N>(a, rhs, sol);
+    square_pinv_solve<N>(a, rhs, sol, allow_lu);
 }
 template <int M, int N>
 __device__ __forceinline__ typename std::enable_if<M != N>::type solve_scaled(double (&a)[M * N], double (&v)[N * N],
                                                                              double (&w2)[N], const double (&rhs)[M],
-                                                                             double (&sol)[N])
+                                                                             double (&sol)[N], bool)
 {
     jacobi_svd_core<M, N, true>(a, v, w2);
     jacobi_svd_solve<M, N>(a, v, w2, rhs, sol);
@@ -100,6 +101,7 @@ struct OpLinsolveSVD
     const double *A;
     const double *b;
     double *x;
+    bool allow_lu;
     template <class IO>
     __device__ __forceinline__ void operator()(const IO &io) const
     {
@@ -108,7 +110,7 @@ struct OpLinsolveSVD
         io.load(b, rhs);
         const int shift = pow2_shift(a);
         pow2_rescale(a, shift);
-        solve_scaled(a, v, w2, rhs, sol);
+        solve_scaled(a, v, w2, rhs, sol, allow_lu);
         pow2_rescale(sol, shift); // (A 2^-shift)^+ b = 2^shift A^+ b
         io.store(x, sol);
     }
@@ -423,12 +425,12 @@ int ppx_cuda_batch_linsolve_svd(int m, int n, const double *A, const double *b, 
     if (count == 0)
         return PPX_OK;
     PPX_CHECK_PTRS(A, b, x);
-    PPX_SHAPE2(6, 6, dispatch(layout, OpLinsolveSVD<6, 6>{A, b, x}, count, ld, stream));
-    PPX_SHAPE2(4, 3, dispatch(layout, OpLinsolveSVD<4, 3>{A, b, x}, count, ld, stream));
-    PPX_SHAPE2(3, 3, dispatch(layout, OpLinsolveSVD<3, 3>{A, b, x}, count, ld, stream));
-    PPX_SHAPE2(4, 4, dispatch(layout, OpLinsolveSVD<4, 4>{A, b, x}, count, ld, stream));
-    PPX_SHAPE2(5, 4, dispatch(layout, OpLinsolveSVD<5, 4>{A, b, x}, count, ld, stream));
-    PPX_SHAPE2(6, 4, dispatch(layout, OpLinsolveSVD<6, 4>{A, b, x}, count, ld, stream));
+    PPX_SHAPE2(6, 6, dispatch(layout, OpLinsolveSVD<6, 6>{A, b, x, g_ppx_square_lu.load(std::memory_order_relaxed) != 0}, count, ld, stream));
+    PPX_SHAPE2(4, 3, dispatch(layout, OpLinsolveSVD<4, 3>{A, b, x, g_ppx_square_lu.load(std::memory_order_relaxed) != 0}, count, ld, stream));
+    PPX_SHAPE2(3, 3, dispatch(layout, OpLinsolveSVD<3, 3>{A, b, x, g_ppx_square_lu.load(std::memory_order_relaxed) != 0}, count, ld, stream));
+    PPX_SHAPE2(4, 4, dispatch(layout, OpLinsolveSVD<4, 4>{A, b, x, g_ppx_square_lu.load(std::memory_order_relaxed) != 0}, count, ld, stream));
+    PPX_SHAPE2(5, 4, dispatch(layout, OpLinsolveSVD<5, 4>{A, b, x, g_ppx_square_lu.load(std::memory_order_relaxed) != 0}, count, ld, stream));
+    PPX_SHAPE2(6, 4, dispatch(layout, OpLinsolveSVD<6, 4>{A, b, x, g_ppx_square_lu.load(std::memory_order_relaxed) != 0}, count, ld, stream));
     return PPX_ERR_BAD_SHAPE;
 }
 

@@ -6,6 +6,7 @@
 #include "ppx_launch.cuh"
 
 std::atomic<uint64_t> g_ppx_launch_count{0};
+std::atomic<int> g_ppx_square_lu{1};
 
 namespace
 {
@@ -137,6 +138,7 @@ int ppx_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream)
 int ppx_cuda_stream_synchronize(void *stream) { return (int)cudaStreamSynchronize((cudaStream_t)stream); }
 
 uint64_t ppx_cuda_launch_count(void) { return g_ppx_launch_count.load(std::memory_order_relaxed); }
+int ppx_cuda_set_square_solve_lu(int enable) { return g_ppx_square_lu.exchange(enable != 0 ? 1 : 0); }
 
 int ppx_cuda_aos_to_soa(const double *aos, double *soa, int width, size_t n, size_t ld, void *stream)
 {

@@ -180,7 +180,7 @@ class EigSym4(Workload):
 
 
 class IkNewtonStep(Workload):
-    """config 5: UR5 IK Newton step (FK + Jacobian + log + adjoint + SVD pseudo-inverse solve)"""
+    """config 5: UR5 IK Newton step (FK + Jacobian + log + adjoint + linsolve<SVD>: LU fast path, Jacobi SVD fallback)"""
     name = "ik_newton_step"
     n_default = 1 << 25  # 256M over 8 GPUs
     bytes_in, bytes_out = 48 + 128, 48
@@ -188,8 +188,9 @@ class IkNewtonStep(Workload):
 
     def setup(self):
         self.kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
-        q = _device_records(self.n, 6, synth.SEEDS[self.name], self.first, -np.pi, np.pi, self.device)
-        d = _device_records(self.n, 6, synth.SEEDS[self.name] ^ 0xA5A5, self.first, -0.05, 0.05, self.device)
+        seed = synth.SEEDS[getattr(self, "seed_name", self.name)]
+        q = _device_records(self.n, 6, seed, self.first, -np.pi, np.pi, self.device)
+        d = _device_records(self.n, 6, seed ^ 0xA5A5, self.first, -0.05, 0.05, self.device)
         self.q = mb.to_soa(q)
         qd = mb.to_soa(q + d)
         del q, d
@@ -199,6 +200,20 @@ class IkNewtonStep(Workload):
 
     def step(self):
         self.kin.ik_newton_step(self.q, self.Tt, layout=mb.SOA, out=self.qo)
+
+
+class IkNewtonStepSvd(IkNewtonStep):
+    """config 5 with the pseudo-inverse solve forced through the Jacobi SVD on every instance (the fp64-bound variant)"""
+    name = "ik_newton_step_svd"
+    seed_name = "ik_newton_step"
+
+    def step(self):
+        from . import _lib
+        prev = _lib.set_square_solve_lu(False)
+        try:
+            self.kin.ik_newton_step(self.q, self.Tt, layout=mb.SOA, out=self.qo)
+        finally:
+            _lib.set_square_solve_lu(prev)
 
 
 
@@ -221,4 +236,4 @@ class IkCodo(Workload):
         self.out = self.kin.inverseSpace(self.Tt, self.q0, self.lo, self.hi)
 
 
-WORKLOADS = {w.name: w for w in (Ur5FkJacobian, Ur5FkJacobianAoS, Se3ExpLog, LinsolveQR43, Svd66, EigSym4, IkNewtonStep, IkCodo)}
+WORKLOADS = {w.name: w for w in (Ur5FkJacobian, Ur5FkJacobianAoS, Se3ExpLog, LinsolveQR43, Svd66, EigSym4, IkNewtonStep, IkNewtonStepSvd, IkCodo)}

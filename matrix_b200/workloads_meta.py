@@ -12,5 +12,6 @@ META = {
     "svd_6x6": {"cpu_sample": 1 << 22},
     "eig_sym_4": {"cpu_sample": 1 << 23},
     "ik_newton_step": {"cpu_sample": 1 << 21},
+    "ik_newton_step_svd": {"cpu_sample": 1 << 21},
     "inverse_space_codo": {"cpu_sample": 1 << 19},
 }

@@ -840,3 +840,56 @@ def test_persistent_and_staged_kernels_stay_inside_their_buffers(mb, port, n):
         assert np.all(rel_err(inside(wi, 36), ref_inv) <= REL * np.maximum(1.0, kappa))
         assert np.all(rel_err(inside(wl, 6), ref_x) <= REL * np.maximum(1.0, kappa))
         assert torch.all(ist[:pad] == -3) and torch.all(ist[pad + n:] == -3) and torch.all(ist[pad:pad + n] == 0)
+
+
+# --------------------------------------------------------------------------------------- square linsolve<SVD>: LU fast path
+def test_square_pinv_solve_fast_path_and_fallback(mb, port, fixtures):
+    """Square linsolve<SVD> systems and the IK Newton step take LU with partial pivoting unless a pivot is below 1e-8 of
+    the largest; then the Jacobi SVD solve.  Both paths against the oracle's SVD::solve, the forced-SVD mode against
+    the default one, and inputs that must take the fallback (near-singular Jacobians, the rank-deficient fixtures)."""
+    from matrix_b200 import _lib
+    n = 1 << 14
+    S, M = synth.UR5_SCREWS, synth.UR5_HOME
+    kin = mb.Kinematics(S, M)
+    q, Tt, kappa = _ik_inputs(port, n, first=77)
+    # near-singular configurations: wrist (q5 -> 0) and elbow (q3 -> 0) at distances 1e-3 .. 1e-11
+    qs = q[:512].copy()
+    qs[:256, 4] = 10.0 ** -np.linspace(3, 11, 256)
+    qs[256:, 2] = 10.0 ** -np.linspace(3, 11, 256)
+    Ts = port.poe_fk_jacobian(S, M, qs + synth.ik_offsets(512), want_Js=False)[0]
+    Js = port.poe_fk_jacobian(S, M, qs, want_T=False)[1]
+    sv = np.linalg.svd(Js.reshape(512, 6, 6).transpose(0, 2, 1), compute_uv=False)
+    ks = sv[:, 0] / sv[:, -1]
+    assert ks.max() > 1e9 and ks.min() < 1e5  # both sides of the pivot test
+    A6, b6 = synth.dense(n, 6, 6, seed=0xE1), synth.dense(n, 6, 1, seed=0xE2)
+    k6 = np.linalg.cond(A6.reshape(n, 6, 6).transpose(0, 2, 1))
+    fxA, fxb = fixtures["dense6.A"], fixtures["dense6.b"]
+    out = {}
+    try:
+        for mode in (True, False):
+            _lib.set_square_solve_lu(mode)
+            out[mode] = (
+                run(mb, lambda q_, t_, layout: kin.ik_newton_step(q_, t_, layout=layout), "soa", q, Tt),
+                run(mb, lambda q_, t_, layout: kin.ik_newton_step(q_, t_, layout=layout), "aos", qs, Ts),
+                run(mb, lambda a_, b_, layout: mb.linsolve(mb.SVD, 6, 6, a_, b_, layout=layout), "soa", A6, b6)[0],
+                run(mb, lambda a_, b_, layout: mb.linsolve(mb.SVD, 6, 6, a_, b_, layout=layout), "aos", fxA, fxb)[0])
+    finally:
+        _lib.set_square_solve_lu(True)
+    rq = port.ik_newton_step(S, M, q, Tt)[0]
+    rqs = port.ik_newton_step(S, M, qs, Ts)[0]
+    rx = port.linsolve_svd(6, 6, A6, b6)
+    for mode in (True, False):
+        dq, dqs, x, xf = out[mode]
+        assert np.all(np.abs(dq - rq).max(axis=1) <= 1e-12 * kappa * np.maximum(1.0, np.abs(rq - q).max(axis=1)))
+        step = np.maximum(1.0, np.abs(rqs - qs).max(axis=1))
+        assert np.all(np.abs(dqs - rqs).max(axis=1) <= 1e-11 * ks * step)
+        assert np.all(rel_err(x, rx) <= REL * np.maximum(1.0, k6))
+        # the recorded reference outputs incl. zero / rank-deficient / Hilbert matrices (truncation active): the fallback
+        ref = fixtures["dense6.x_svd"]
+        ok = np.isfinite(ref).all(axis=1)
+        kf = np.linalg.cond(fxA[ok].reshape(-1, 6, 6).transpose(0, 2, 1))
+        good = kf < 1e12
+        assert np.all(rel_err(xf[ok][good], ref[ok][good]) <= 1e-11 * np.maximum(1.0, kf[good]))
+    # the two modes agree far inside the parity bar on well-conditioned systems
+    well = kappa < 1e3
+    assert np.abs(out[True][0][well] - out[False][0][well]).max() < 1e-11
