@@ -120,10 +120,14 @@ __device__ __forceinline__ void ik_newton_update(const ChainConst<NJ> &ch, const
 }
 
 // BASELINE config 5.  48 + 128 B in, 48 B out, ~10 kflop: fp64-bound.
+// 3 CTAs per SM (168 registers): +4 % over 2 now that the common path is the LU solve; the Jacobi fallback spills 48 B
+#ifndef PPX_IK_MINB
+#define PPX_IK_MINB 3
+#endif
 template <int NJ>
 struct OpIkStep
 {
-    static constexpr int BLOCK = 128, MINB = 1, MAXW = 16;
+    static constexpr int BLOCK = 128, MINB = PPX_IK_MINB, MAXW = 16;
     ChainConst<NJ> ch;
     const double *q;
     const double *Tt;
@@ -195,7 +199,7 @@ struct IkSolveArgs
 };
 
 template <int LAYOUT>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, PPX_IK_MINB)
     ik_solve_kernel(const __grid_constant__ IkSolveArgs a, size_t n, size_t ld, unsigned long long *next)
 {
     constexpr int NJ = 6;

@@ -1091,29 +1091,34 @@ PPX_DEV void jacobi_rowsolve(const double (&A)[N * N], const double (&b)[N], dou
 template <int N>
 PPX_DEV void square_pinv_solve(const double (&A)[N * N], const double (&b)[N], double (&x)[N], bool allow_lu)
 {
-    double lu[N * N], rx[N];
-#pragma unroll
-    for (int i = 0; i < N * N; i++)
-        lu[i] = A[i];
+    double rx[N];
 #pragma unroll
     for (int i = 0; i < N; i++)
         rx[i] = b[i];
-    bool even;
-    lu_factor_solve<N, 1>(lu, rx, even);
-    double pmax = 0.0;
-#pragma unroll
-    for (int k = 0; k < N; k++)
-        pmax = fmax(pmax, fabs(lu[k + k * N]));
-    bool easy = allow_lu;
-#pragma unroll
-    for (int k = 0; k < N; k++)
-        easy = easy && fabs(lu[k + k * N]) > 1e-8 * pmax;
-    if (__all_sync(0xffffffffu, easy))
+    bool easy = false;
+    if (allow_lu) // uniform over the launch
     {
+        double lu[N * N];
 #pragma unroll
-        for (int i = 0; i < N; i++)
-            x[i] = rx[i];
-        return;
+        for (int i = 0; i < N * N; i++)
+            lu[i] = A[i];
+        bool even;
+        lu_factor_solve<N, 1>(lu, rx, even);
+        double pmax = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            pmax = fmax(pmax, fabs(lu[k + k * N]));
+        easy = true;
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            easy = easy && fabs(lu[k + k * N]) > 1e-8 * pmax;
+        if (__all_sync(0xffffffffu, easy))
+        {
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                x[i] = rx[i];
+            return;
+        }
     }
     double xs[N];
     jacobi_rowsolve<N>(A, b, xs);

@@ -97,17 +97,41 @@ __device__ __forceinline__ typename std::enable_if<M != N>::type solve_scaled(do
 template <int M, int N>
 struct OpLinsolveSVD
 {
-    static constexpr int BLOCK = 128, MINB = 1, MAXW = M * N;
+    static constexpr int BLOCK = 128, MINB = (M == N ? 2 : 1), MAXW = M * N;
     const double *A;
     const double *b;
     double *x;
     bool allow_lu;
+    // square systems mostly take the LU path and are then bound by their 8 (n^2 + 2n) bytes: inputs staged with cp.async
+    // like OpLinsolveLU's
+    static constexpr bool PREFETCH = (M == N);
+    static constexpr int IN_WIDTH = M * N + M + 2;
+    template <class IO>
+    __device__ __forceinline__ void prefetch(const IO &io, double *stage) const
+    {
+        io.template async_load<M * N>(A, stage);
+        io.template async_load<M>(b, stage + IO::stage_doubles(BLOCK, M * N));
+    }
+    template <class IO>
+    __device__ __forceinline__ void compute_store(const IO &io, const double *stage) const
+    {
+        double a[M * N], rhs[M];
+        io.template read_staged<M * N>(stage, a);
+        io.template read_staged<M>(stage + IO::stage_doubles(BLOCK, M * N), rhs);
+        solve_store(io, a, rhs);
+    }
     template <class IO>
     __device__ __forceinline__ void operator()(const IO &io) const
     {
-        double a[M * N], v[N * N], w2[N], rhs[M], sol[N];
+        double a[M * N], rhs[M];
         io.load(A, a);
         io.load(b, rhs);
+        solve_store(io, a, rhs);
+    }
+    template <class IO>
+    __device__ __forceinline__ void solve_store(const IO &io, double (&a)[M * N], const double (&rhs)[M]) const
+    {
+        double v[N * N], w2[N], sol[N];
         const int shift = pow2_shift(a);
         pow2_rescale(a, shift);
         solve_scaled(a, v, w2, rhs, sol, allow_lu);
