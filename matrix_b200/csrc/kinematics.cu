@@ -134,13 +134,39 @@ struct OpIkStep
     double *q_out;
     double *Vs;
     bool allow_lu;
+#ifndef PPX_IK_PREFETCH
+#define PPX_IK_PREFETCH 1
+#endif
+    // joint angles and target pose of the next tile staged (cp.async) behind the arithmetic of the current one
+    static constexpr bool PREFETCH = PPX_IK_PREFETCH != 0;
+    static constexpr int IN_WIDTH = NJ + 16 + 2;
+    template <class IO>
+    __device__ __forceinline__ void prefetch(const IO &io, double *stage) const
+    {
+        io.template async_load<NJ>(q, stage);
+        io.template async_load<16>(Tt, stage + IO::stage_doubles(BLOCK, NJ));
+    }
+    template <class IO>
+    __device__ __forceinline__ void compute_store(const IO &io, const double *stage) const
+    {
+        double qi[NJ], m[16];
+        io.template read_staged<NJ>(stage, qi);
+        io.template read_staged<16>(stage + IO::stage_doubles(BLOCK, NJ), m);
+        step_store(io, qi, m);
+    }
     template <class IO>
     __device__ __forceinline__ void operator()(const IO &io) const
     {
-        double qi[NJ], m[16], vs[6];
-        Rigid target;
+        double qi[NJ], m[16];
         io.load(q, qi);
         io.load(Tt, m);
+        step_store(io, qi, m);
+    }
+    template <class IO>
+    __device__ __forceinline__ void step_store(const IO &io, double (&qi)[NJ], const double (&m)[16]) const
+    {
+        double vs[6];
+        Rigid target;
         rigid_from_record(m, target);
         ik_newton_update<NJ>(ch, target, qi, vs, allow_lu);
         io.store(q_out, qi);
