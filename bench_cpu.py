@@ -170,7 +170,7 @@ def cpu_op(name, oracle, n):
         return lambda: _ok(oracle.lib.ppxo_ik_solve(_d(S), _d(M), C.c_int(6), _d(q), _d(Tt), C.c_int(20), _d(qo),
                                                     it.ctypes.data_as(C.POINTER(C.c_int)), C.c_size_t(n), C.c_int(NTHREADS)))
     m, nn = {"linsolve_svd_6x6": (6, 6), "linsolve_lu_6x6": (6, 6), "inverse_6x6": (6, 6), "det_6x6": (6, 6),
-             "pinv_4x3": (4, 3), "norm2_6x6": (6, 6), "svd_4x3": (4, 3)}[name]
+             "pinv_4x3": (4, 3), "pinv_6x6": (6, 6), "norm2_6x6": (6, 6), "svd_4x3": (4, 3)}[name]
     A = synth.dense(n, m, nn, seed=0x301)
     b = synth.dense(n, m, 1, seed=0x302)
     st = np.empty(n, dtype=np.int8)
@@ -190,6 +190,9 @@ def cpu_op(name, oracle, n):
     if name == "pinv_4x3":
         x = np.empty((n, 12)); _touch(x)
         return lambda: _ok(oracle.lib.ppxo_pinv(C.c_int(4), C.c_int(3), _d(A), _d(x), C.c_size_t(n), C.c_int(NTHREADS)))
+    if name == "pinv_6x6":
+        x = np.empty((n, 36)); _touch(x)
+        return lambda: _ok(oracle.lib.ppxo_pinv(C.c_int(6), C.c_int(6), _d(A), _d(x), C.c_size_t(n), C.c_int(NTHREADS)))
     if name == "norm2_6x6":
         x = np.empty(n); _touch(x)
         return lambda: _ok(oracle.lib.ppxo_norm2(C.c_int(6), C.c_int(6), _d(A), _d(x), C.c_size_t(n), C.c_int(NTHREADS)))

@@ -655,11 +655,14 @@ PPX_DEV bool lu_factor_solve(double (&A)[N * N], double (&B)[N * (NRHS > 0 ? NRH
 // the reference's, and the inverse overwrites A -- 36 live doubles for n = 6 instead of 72 for "factor + 6 right-hand
 // sides", which is what lets this HBM-bound kernel run 4 CTAs per SM instead of 2.  Row exchanges are predicated swaps
 // (compile-time indices only); they come back as column exchanges of the result, last first: A^-1 = (P A)^-1 P.
+// pmin / pmax: smallest and largest pivot magnitude met (the conditioning guard of the square pinv, solvers.cu)
 template <int N>
-PPX_DEV bool gauss_jordan_inverse(double (&A)[N * N])
+PPX_DEV bool gauss_jordan_inverse(double (&A)[N * N], double &pmin, double &pmax)
 {
     bool singular = false;
     int piv[N];
+    pmin = DBL_MAX;
+    pmax = 0.0;
 #pragma unroll
     for (int k = 0; k < N; k++)
     {
@@ -674,6 +677,8 @@ PPX_DEV bool gauss_jordan_inverse(double (&A)[N * N])
             ip = better ? r : ip;
         }
         singular |= valmax < EPS_DP;
+        pmin = valmax < pmin ? valmax : pmin; // a NaN pivot leaves both untouched; the caller's test then fails on pmax
+        pmax = valmax > pmax ? valmax : pmax;
         piv[k] = ip;
 #pragma unroll
         for (int r = k + 1; r < N; r++)
@@ -721,6 +726,12 @@ PPX_DEV bool gauss_jordan_inverse(double (&A)[N * N])
         }
     }
     return singular;
+}
+template <int N>
+PPX_DEV bool gauss_jordan_inverse(double (&A)[N * N])
+{
+    double pmin, pmax;
+    return gauss_jordan_inverse<N>(A, pmin, pmax);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -318,13 +318,42 @@ struct OpPinv
     static constexpr int BLOCK = 128, MINB = (M * N >= 36 ? 1 : 3), MAXW = M * N;
     const double *A;
     double *P; // N x M
+    bool allow_lu;
+    // A square matrix whose pivots all lie within 1e-8 of the largest is inverted by Gauss-Jordan elimination: the
+    // truncation below cannot act before cond ~ 2e15, so pinv(A) = A^-1 there (the argument of square_pinv_solve)
+    template <class IO, int MM = M>
+    __device__ __forceinline__ typename std::enable_if<MM == N, bool>::type fast_square(const IO &io, const double (&a)[M * N],
+                                                                                      int shift, double (&g)[N * M]) const
+    {
+        if (!allow_lu)
+            return false;
+#pragma unroll
+        for (int i = 0; i < N * N; i++)
+            g[i] = a[i];
+        double pmin, pmax;
+        gauss_jordan_inverse<N>(g, pmin, pmax);
+        const bool easy = pmin > 1e-8 * pmax && pmax < DBL_MAX; // false for zero, inf and NaN pivots
+        pow2_rescale(g, shift);
+        if (__all_sync(0xffffffffu, easy))
+            io.store(P, g);
+        return easy;
+    }
+    template <class IO, int MM = M>
+    __device__ __forceinline__ typename std::enable_if<MM != N, bool>::type fast_square(const IO &, const double (&)[M * N], int,
+                                                                                      double (&)[N * M]) const
+    {
+        return false;
+    }
     template <class IO>
     __device__ __forceinline__ void operator()(const IO &io) const
     {
-        double a[M * N], v[N * N], w2[N], p[N * M];
+        double a[M * N], v[N * N], w2[N], p[N * M], g[N * M];
         io.load(A, a);
         const int shift = pow2_shift(a);
         pow2_rescale(a, shift);
+        const bool easy = fast_square(io, a, shift, g);
+        if (M == N && __all_sync(0xffffffffu, easy))
+            return; // stored by fast_square
         jacobi_svd_core<M, N, true>(a, v, w2);
         double wmax2 = w2[0];
 #pragma unroll
@@ -350,6 +379,12 @@ struct OpPinv
             }
         }
         pow2_rescale(p, shift); // (A 2^-shift)^+ = 2^shift A^+
+        if (M == N)
+        {
+#pragma unroll
+            for (int i = 0; i < N * M; i++)
+                p[i] = easy ? g[i] : p[i];
+        }
         io.store(P, p);
     }
 };
@@ -529,12 +564,12 @@ int ppx_cuda_batch_pinv(int m, int n, const double *A, double *P, size_t count, 
     if (count == 0)
         return PPX_OK;
     PPX_CHECK_PTRS(A, P);
-    PPX_SHAPE2(6, 6, dispatch(layout, OpPinv<6, 6>{A, P}, count, ld, stream));
-    PPX_SHAPE2(4, 3, dispatch(layout, OpPinv<4, 3>{A, P}, count, ld, stream));
-    PPX_SHAPE2(3, 3, dispatch(layout, OpPinv<3, 3>{A, P}, count, ld, stream));
-    PPX_SHAPE2(4, 4, dispatch(layout, OpPinv<4, 4>{A, P}, count, ld, stream));
-    PPX_SHAPE2(5, 4, dispatch(layout, OpPinv<5, 4>{A, P}, count, ld, stream));
-    PPX_SHAPE2(6, 4, dispatch(layout, OpPinv<6, 4>{A, P}, count, ld, stream));
+    PPX_SHAPE2(6, 6, dispatch(layout, OpPinv<6, 6>{A, P, g_ppx_square_lu.load(std::memory_order_relaxed) != 0}, count, ld, stream));
+    PPX_SHAPE2(4, 3, dispatch(layout, OpPinv<4, 3>{A, P, g_ppx_square_lu.load(std::memory_order_relaxed) != 0}, count, ld, stream));
+    PPX_SHAPE2(3, 3, dispatch(layout, OpPinv<3, 3>{A, P, g_ppx_square_lu.load(std::memory_order_relaxed) != 0}, count, ld, stream));
+    PPX_SHAPE2(4, 4, dispatch(layout, OpPinv<4, 4>{A, P, g_ppx_square_lu.load(std::memory_order_relaxed) != 0}, count, ld, stream));
+    PPX_SHAPE2(5, 4, dispatch(layout, OpPinv<5, 4>{A, P, g_ppx_square_lu.load(std::memory_order_relaxed) != 0}, count, ld, stream));
+    PPX_SHAPE2(6, 4, dispatch(layout, OpPinv<6, 4>{A, P, g_ppx_square_lu.load(std::memory_order_relaxed) != 0}, count, ld, stream));
     return PPX_ERR_BAD_SHAPE;
 }
 

@@ -122,6 +122,8 @@ def make_ops(layout=mb.SOA):
              lambda A, b, o, s, c: lib.ppx_cuda_batch_det(6, _p(A), _p(o[0]), *tail(c)), [1])
     dense_op("pinv_4x3", 4, 3, 1 << 24, 0x209, 8 * 24, "linalg.hpp:1211-1227",
              lambda A, b, o, s, c: lib.ppx_cuda_batch_pinv(4, 3, _p(A), _p(o[0]), *tail(c)), [12])
+    dense_op("pinv_6x6", 6, 6, 1 << 24, 0x20F, 8 * 72, "linalg.hpp:1211-1227",
+             lambda A, b, o, s, c: lib.ppx_cuda_batch_pinv(6, 6, _p(A), _p(o[0]), *tail(c)), [36])
     dense_op("norm2_6x6", 6, 6, 1 << 23, 0x20B, 8 * 37, "linalg.hpp:926-931",
              lambda A, b, o, s, c: lib.ppx_cuda_batch_norm2(6, 6, _p(A), _p(o[0]), *tail(c)), [1])
     dense_op("svd_4x3", 4, 3, 1 << 24, 0x20D, 8 * (12 + 12 + 3 + 9), "linalg.hpp:605-884",

@@ -872,14 +872,18 @@ def test_square_pinv_solve_fast_path_and_fallback(mb, port, fixtures):
                 run(mb, lambda q_, t_, layout: kin.ik_newton_step(q_, t_, layout=layout), "soa", q, Tt),
                 run(mb, lambda q_, t_, layout: kin.ik_newton_step(q_, t_, layout=layout), "aos", qs, Ts),
                 run(mb, lambda a_, b_, layout: mb.linsolve(mb.SVD, 6, 6, a_, b_, layout=layout), "soa", A6, b6)[0],
-                run(mb, lambda a_, b_, layout: mb.linsolve(mb.SVD, 6, 6, a_, b_, layout=layout), "aos", fxA, fxb)[0])
+                run(mb, lambda a_, b_, layout: mb.linsolve(mb.SVD, 6, 6, a_, b_, layout=layout), "aos", fxA, fxb)[0],
+                run(mb, lambda a_, layout: mb.pinv(6, 6, a_, layout=layout), "soa", A6),
+                run(mb, lambda a_, layout: mb.pinv(6, 6, a_, layout=layout), "aos", fxA))
     finally:
         _lib.set_square_solve_lu(True)
     rq = port.ik_newton_step(S, M, q, Tt)[0]
     rqs = port.ik_newton_step(S, M, qs, Ts)[0]
     rx = port.linsolve_svd(6, 6, A6, b6)
+    rP, rPf = port.pinv(6, 6, A6), port.pinv(6, 6, fxA)
     for mode in (True, False):
-        dq, dqs, x, xf = out[mode]
+        dq, dqs, x, xf, P, Pf = out[mode]
+        assert np.all(rel_err(P, rP) <= REL * np.maximum(1.0, k6))
         assert np.all(np.abs(dq - rq).max(axis=1) <= 1e-12 * kappa * np.maximum(1.0, np.abs(rq - q).max(axis=1)))
         step = np.maximum(1.0, np.abs(rqs - qs).max(axis=1))
         assert np.all(np.abs(dqs - rqs).max(axis=1) <= 1e-11 * ks * step)
@@ -890,6 +894,15 @@ def test_square_pinv_solve_fast_path_and_fallback(mb, port, fixtures):
         kf = np.linalg.cond(fxA[ok].reshape(-1, 6, 6).transpose(0, 2, 1))
         good = kf < 1e12
         assert np.all(rel_err(xf[ok][good], ref[ok][good]) <= 1e-11 * np.maximum(1.0, kf[good]))
+        okp = np.isfinite(rPf).all(axis=1)  # pinv of the same fixtures: zero, identity, rank 4, rank 1, Hilbert ...
+        kp = np.linalg.cond(fxA[okp].reshape(-1, 6, 6).transpose(0, 2, 1))
+        goodp = kp < 1e12
+        assert np.all(rel_err(Pf[okp][goodp], rPf[okp][goodp]) <= 1e-11 * np.maximum(1.0, kp[goodp]))
+        rank_def = okp.copy()
+        rank_def[okp] = kp > 1e15  # truncation active: the SVD fallback must have been taken
+        if rank_def.any():
+            nz = np.abs(rPf[rank_def]).max(axis=1) > 0
+            assert np.all(rel_err(Pf[rank_def][nz], rPf[rank_def][nz]) < 1e-6)
     # the two modes agree far inside the parity bar on well-conditioned systems
     well = kappa < 1e3
     assert np.abs(out[True][0][well] - out[False][0][well]).max() < 1e-11
