@@ -311,7 +311,7 @@ def main():
     c_head = counters.get(args.workload, {})
     traffic = c_head.get("dram_bytes_per_launch") if c_head.get("instances") == n else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": f"batch_kernel<SOA, {cls.__name__}>",
+                "traffic": traffic, "peak_source": peak_src, "kernel": cls.kernel,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_instance": cls.bytes_per_instance(),
                 "instances_per_launch": n}
 
@@ -413,7 +413,7 @@ def main():
             "metric": "instances/sec", "value": value, "unit": "instances/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "instances_per_gpu": n, "layout": "soa (device resident)",
+            "config": {"workload": args.workload, "instances_per_gpu": n, "layout": f"{cls.layout} (device resident)",
                        "chain": "UR5 (test/lie_test.cpp:187-196)" if "ur5" in args.workload or "ik" in args.workload or "inverse" in args.workload
                        else None,
                        "l2": f"inputs+outputs {n * cls.bytes_per_instance() / 1e6:.0f} MB per step >> 126 MB L2, "

@@ -22,6 +22,8 @@ def _device_records(n, width, seed, first, lo, hi, device):
 
 class Workload:
     name = ""
+    kernel = ""  # the kernel one step() launches
+    layout = "soa"  # device layout of the batch: component planes, or "aos" = arrays of the reference's records
     n_default = 0
     bytes_in = 0      # algorithmic bytes per instance
     bytes_out = 0
@@ -38,6 +40,7 @@ class Workload:
 class Ur5FkJacobian(Workload):
     """config 2: UR5 product-of-exponentials forward kinematics + space Jacobian"""
     name = "ur5_fk_jacobian"
+    kernel = "batch_kernel_pf<SOA, OpFkJacobian<6, true, true>>"
     n_default = 1 << 24
     bytes_in, bytes_out = 48, 128 + 288
 
@@ -71,6 +74,8 @@ class Ur5FkJacobian(Workload):
 class Ur5FkJacobianAoS(Ur5FkJacobian):
     """config 2 on the drop-in layout: device-resident arrays of dense reference records (std::vector<MatrixS>)"""
     name = "ur5_fk_jacobian_aos"
+    kernel = "batch_kernel_pf<AOS, OpFkJacobian<6, true, true>>"
+    layout = "aos"
 
     def setup(self):
         self.kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
@@ -85,6 +90,7 @@ class Ur5FkJacobianAoS(Ur5FkJacobian):
 class Se3ExpLog(Workload):
     """config 1: se3::exp -> SE3::log round trip, fused"""
     name = "se3_exp_log"
+    kernel = "batch_kernel_pf<SOA, OpSe3ExpLog>"
     n_default = 1 << 26  # the 1M-instance case of BASELINE fits in L2; 64M is the HBM-resident size
     bytes_in, bytes_out = 48, 48
 
@@ -109,6 +115,7 @@ class Se3ExpLog(Workload):
 class LinsolveQR43(Workload):
     """config 3: least-squares linsolve<QR> on 4x3"""
     name = "linsolve_qr_4x3"
+    kernel = "batch_kernel<SOA, OpLinsolveQR<4, 3>>"
     n_default = 1 << 26
     bytes_in, bytes_out = 96 + 32, 24 + 1
 
@@ -133,6 +140,7 @@ class LinsolveQR43(Workload):
 class Svd66(Workload):
     """config 4a: SVD<6,6> (U, w, V)"""
     name = "svd_6x6"
+    kernel = "batch_kernel<SOA, OpSVD<6, 6>>"
     n_default = 1 << 24
     bytes_in, bytes_out = 288, 288 + 48 + 288
     bound = "fp64"
@@ -157,6 +165,7 @@ class Svd66(Workload):
 class EigSym4(Workload):
     """config 4b: EigenValue<4>(S, sorted=true) with eigenvectors"""
     name = "eig_sym_4"
+    kernel = "batch_kernel<SOA, OpEigSym<4, true>>"
     n_default = 1 << 24
     bytes_in, bytes_out = 128, 32 + 128
     bound = "fp64"
@@ -182,6 +191,7 @@ class EigSym4(Workload):
 class IkNewtonStep(Workload):
     """config 5: UR5 IK Newton step (FK + Jacobian + log + adjoint + linsolve<SVD>: LU fast path, Jacobi SVD fallback)"""
     name = "ik_newton_step"
+    kernel = "batch_kernel_pf<SOA, OpIkStep<6>>"
     n_default = 1 << 25  # 256M over 8 GPUs
     bytes_in, bytes_out = 48 + 128, 48
     bound = "fp64"
@@ -205,6 +215,7 @@ class IkNewtonStep(Workload):
 class IkNewtonStepSvd(IkNewtonStep):
     """config 5 with the pseudo-inverse solve forced through the Jacobi SVD on every instance (the fp64-bound variant)"""
     name = "ik_newton_step_svd"
+    kernel = "batch_kernel_pf<SOA, OpIkStep<6>> (allow_lu = false)"
     seed_name = "ik_newton_step"
 
     def step(self):
@@ -221,6 +232,8 @@ class IkCodo(Workload):
     """SURVEY 8(f) row 4: kinematics<6>::inverseSpace, the trust-region IK the reference's demo and benchmark time
     (demo/main.cpp:371-377, benchmark/benchmark.cpp:167-189): start 0.05 rad off the solution on every joint"""
     name = "inverse_space_codo"
+    kernel = "ik_codo_kernel<AOS>"
+    layout = "aos"
     n_default = 1 << 24  # as config 2; the ~0.3 % of targets on which CoDo stalls for ITMAX = 300 trips leave a ~10 ms tail per launch
     bytes_in, bytes_out = 48 + 128, 48 + 8 + 1
     bound = "fp64 / latency (data-dependent iteration counts)"
