@@ -139,3 +139,25 @@ def test_two_rank_sharding_reassembles_the_batch(tmp_path):
     full = np.load(tmp_path / "gathered.npy")
     assert np.array_equal(full, synth.joint_angles(n_total))  # bitwise the single-process batch
     assert np.load(tmp_path / "tmax.npy")[0] == 2.0
+
+
+def test_reference_arm_of_the_bench_runs_on_the_host():
+    """`bench.py --impl reference` (the arm the driver times beside the GPU arm) needs no GPU: one JSON line with the
+    contract's keys, metric and config of the GPU arm, zero GPU launches."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--n", "65536"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "instances/sec" and d["unit"] == "instances/s"
+    assert d["config"]["workload"] == "ur5_fk_jacobian" and d["value"] > 0 and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d.get("gpu_launches", 0) == 0
