@@ -13,6 +13,8 @@ Tolerances (fp64, north_star: 1e-12 relative):
   SVD / eig: sorted singular values / eigenvalues relative to the largest, reconstruction residual,
   orthogonality; vectors only up to sign.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -906,3 +908,30 @@ def test_square_pinv_solve_fast_path_and_fallback(mb, port, fixtures):
     # the two modes agree far inside the parity bar on well-conditioned systems
     well = kappa < 1e3
     assert np.abs(out[True][0][well] - out[False][0][well]).max() < 1e-11
+
+
+# --------------------------------------------------------------------------------------- the bench line itself
+def test_bench_prints_the_contract_line(mb):
+    """bench.py on a small batch: one JSON line with the contract's keys, a roofline that adds up, an end-to-end leg
+    that moved the bytes it claims, and as many launches of this library's kernels as steps."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "4", "--warmup", "3", "--n", "1048576",
+                        "--no-others", "--no-cpu", "--e2e-steps", "1"], capture_output=True, text=True, timeout=600,
+                       cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks"):
+        assert key in d, key
+    assert d["metric"] == "instances/sec" and d["n_gpus"] == 1 and d["steps"] == 4 and d["gpu_launches"] == 4
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    assert abs(rf["achieved"] - 1048576 * 464 / (rf["kernel_ms"] * 1e-3) / 1e9) < 1e-6 * rf["achieved"]
+    assert abs(d["value"] - 1048576 * 4 / (d["ms_per_step"] * 4e-3)) < 1e-6 * d["value"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 1048576 * 48 and e["d2h_bytes_per_step"] == 1048576 * 416 and 0 < e["value"] < d["value"]
