@@ -21,6 +21,34 @@ constexpr double PI = 3.141592653589793;          // include/exprtmpl.hpp:11
 
 #define PPX_DEV __device__ __forceinline__
 
+// Branch-free reciprocal square root / reciprocal: the hardware seed (MUFU.RSQ64H / MUFU.RCP64H, relative
+// error ~2^-22) refined by one third-order step, full fp64 accuracy for normal, non-zero arguments.  Unlike
+// sqrt() and operator/ there is no special-case slow path, hence no call and no convergence barrier in the
+// instruction stream: the independent rotation chains of a Jacobi round stay in one basic block and overlap.
+// (x = 0 gives inf/NaN; callers discard that lane's result with a select.)
+PPX_DEV double rsqrt_nr(double x)
+{
+    double y;
+#ifdef __CUDA_ARCH__
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+    y = (double)(float)(1.0 / sqrt(x)); // host build of the device math (tests/cpp/codo_host.cpp): a seed of the same quality
+#endif
+    const double e = fma(-(x * y), y, 1.0); // 1 - x y^2
+    return fma(y * e, fma(0.375, e, 0.5), y); // y (1 + e/2 + 3 e^2/8)
+}
+PPX_DEV double rcp_nr(double x)
+{
+    double y;
+#ifdef __CUDA_ARCH__
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+    y = (double)(float)(1.0 / x);
+#endif
+    const double e = fma(-x, y, 1.0); // 1 - x y
+    return fma(y, fma(e, e, e), y);   // y (1 + e + e^2)
+}
+
 // Rigid transform: rotation r (column-major, r[i + 3 j]) and translation p.  An SE3 record is
 // [r0 r1 r2 0 | r3 r4 r5 0 | r6 r7 r8 0 | p0 p1 p2 1] (include/liegroup.hpp:186-200).
 struct Rigid
@@ -146,12 +174,15 @@ PPX_DEV void rigid_adjoint_apply(const Rigid &t, const double (&w)[3], const dou
 PPX_DEV void so3_exp(const double (&w)[3], double (&r)[9])
 {
     const double t2 = fma(w[2], w[2], fma(w[1], w[1], w[0] * w[0]));
-    const double theta = sqrt(t2);
+    // theta = t2 / sqrt(t2) and 1/theta^2 from ONE branch-free reciprocal square root (no sqrt(), no division: both
+    // carry slow-path branches); below the reference's threshold its value is not used
+    const bool tiny = t2 < 1.0e-12; // |theta| < 1e-6
+    const double rth = rsqrt_nr(tiny ? 1.0 : t2);
+    const double theta = tiny ? 0.0 : t2 * rth;
     double s, c;
     sincos(theta, &s, &c);
-    const bool tiny = fabs(theta) < 1.0e-6;
-    const double inv = tiny ? 0.0 : 1.0 / t2;
-    const double a = tiny ? 0.0 : s * theta * inv; // sin(theta)/theta
+    const double inv = tiny ? 0.0 : rth * rth;
+    const double a = tiny ? 0.0 : s * rth; // sin(theta)/theta
     const double b = (1.0 - c) * inv;              // (1-cos(theta))/theta^2
     // I + a W + b W^2,  W^2 = w w^T - theta^2 I,  1 - b theta^2 = cos(theta)
     const double d = tiny ? 1.0 : c;
@@ -199,8 +230,7 @@ PPX_DEV void SO3_log(const double (&r)[9], double (&w)[3])
     {
         const double theta = acos(acosinput);
         // sin(acos(c)) = sqrt((1-c)(1+c)): one sqrt instead of a second transcendental
-        const double st = sqrt((1.0 - acosinput) * (1.0 + acosinput));
-        const double k = theta / (2.0 * st);
+        const double k = 0.5 * theta * rsqrt_nr((1.0 - acosinput) * (1.0 + acosinput)); // theta / (2 sin theta)
         w[0] = (r[5] - r[7]) * k;
         w[1] = (r[6] - r[2]) * k;
         w[2] = (r[1] - r[3]) * k;
@@ -215,12 +245,12 @@ PPX_DEV void se3_exp(const double (&xi)[6], Rigid &t)
     const double w[3] = {xi[0], xi[1], xi[2]};
     const double v[3] = {xi[3], xi[4], xi[5]};
     const double p2 = fma(w[2], w[2], fma(w[1], w[1], w[0] * w[0]));
-    const double phi = sqrt(p2);
-    const bool tiny = fabs(phi) < EPS_SP;
+    const bool tiny = p2 < EPS_SP * EPS_SP; // |phi| < EPS_SP
+    const double iphi = tiny ? 0.0 : rsqrt_nr(tiny ? 1.0 : p2); // 1/phi: phi and 1/phi^2 follow without sqrt() or division
+    const double phi = p2 * iphi;
     double s, c;
     sincos(phi, &s, &c);
-    const double inv = tiny ? 0.0 : 1.0 / p2;
-    const double iphi = phi * inv;        // 1/phi
+    const double inv = iphi * iphi;
     const double a = tiny ? 0.0 : s * iphi;
     const double c1 = (1.0 - c) * inv;
     const double c2 = (phi - s) * inv * iphi;
@@ -253,9 +283,8 @@ PPX_DEV void SE3_log(const Rigid &t, double (&xi)[6])
     if (fabs(ct) < 1.0)
     {
         const double theta = acos(ct);
-        const double st = sqrt((1.0 - ct) * (1.0 + ct));
-        const double ist = 1.0 / (2.0 * st);
-        const double ith = 1.0 / theta;
+        const double ist = 0.5 * rsqrt_nr((1.0 - ct) * (1.0 + ct)); // 1 / (2 sin theta); |ct| < 1 keeps the argument > 0
+        const double ith = rcp_nr(theta);                          // theta >= acos(1 - 2^-53) ~ 1.5e-8
         const double k = theta * ist;
         const double coff1 = (ith - (1.0 + ct) * ist) * ith;
         const double w[3] = {(t.r[5] - t.r[7]) * k, (t.r[6] - t.r[2]) * k, (t.r[1] - t.r[3]) * k};
@@ -540,34 +569,6 @@ PPX_DEV int linsolve_qr(double (&A)[M * N], double (&b)[M], double (&x)[N])
     for (int i = 0; i < N; i++)
         x[i] = singular ? b0[i] : b[i];
     return singular ? 3 : 0;
-}
-
-// Branch-free reciprocal square root / reciprocal: the hardware seed (MUFU.RSQ64H / MUFU.RCP64H, relative
-// error ~2^-22) refined by one third-order step, full fp64 accuracy for normal, non-zero arguments.  Unlike
-// sqrt() and operator/ there is no special-case slow path, hence no call and no convergence barrier in the
-// instruction stream: the independent rotation chains of a Jacobi round stay in one basic block and overlap.
-// (x = 0 gives inf/NaN; callers discard that lane's result with a select.)
-PPX_DEV double rsqrt_nr(double x)
-{
-    double y;
-#ifdef __CUDA_ARCH__
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#else
-    y = (double)(float)(1.0 / sqrt(x)); // host build of the device math (tests/cpp/codo_host.cpp): a seed of the same quality
-#endif
-    const double e = fma(-(x * y), y, 1.0); // 1 - x y^2
-    return fma(y * e, fma(0.375, e, 0.5), y); // y (1 + e/2 + 3 e^2/8)
-}
-PPX_DEV double rcp_nr(double x)
-{
-    double y;
-#ifdef __CUDA_ARCH__
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#else
-    y = (double)(float)(1.0 / x);
-#endif
-    const double e = fma(-x, y, 1.0); // 1 - x y
-    return fma(y, fma(e, e, e), y);   // y (1 + e + e^2)
 }
 
 // LU<n> with partial pivoting, include/linalg.hpp:448-533, in registers.  The pivot row is data dependent, so the
