@@ -172,10 +172,12 @@ int ppx_cuda_batch_norm2(int m, int n, const double *A, double *s, size_t count,
 
 /* ---- host-buffer face: the same operations on HOST arrays of dense reference records (AoS), i.e. on
  * std::vector<ppx::MatrixS<M,N>>::data().  Each call cuts the batch into chunks that rotate over three
- * streams so the H2D copy, the kernel and the D2H copy of neighbouring chunks overlap; device scratch
- * comes from the stream-ordered allocator and is released before returning.  Blocking.  Pinned host
+ * streams so the H2D copy, the kernel and the D2H copy of neighbouring chunks overlap.  Blocking.  Pinned host
  * memory (ppx_cuda_malloc_host) lets the copies run asynchronously; pageable memory works, slower.
- * Optional outputs (T/Js, Vs, iters, status, U, V, z) may be NULL exactly as in the device entry points. */
+ * The streams and up to PPX_HOST_POOL_MIB (environment, default 1024) MiB of device scratch per device are kept
+ * between calls, which is what makes small calls cheap; ppx_cuda_host_trim() returns the scratch to the driver.
+ * Thread-safe.  Optional outputs (T/Js, Vs, iters, status, U, V, z) may be NULL exactly as in the device entry points. */
+int ppx_cuda_host_trim(void);
 int ppx_cuda_host_so3_exp(const double *w, double *R, size_t n);
 int ppx_cuda_host_SO3_log(const double *R, double *w, size_t n);
 int ppx_cuda_host_se3_exp(const double *xi, double *T, size_t n);

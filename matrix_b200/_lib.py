@@ -88,6 +88,7 @@ _SIGNATURES = {
     "ppx_cuda_host_det": [_i, _vp, _vp, _sz],
     "ppx_cuda_host_pinv": [_i, _i, _vp, _vp, _sz],
     "ppx_cuda_host_norm2": [_i, _i, _vp, _vp, _sz],
+    "ppx_cuda_host_trim": [],
 }
 _RESTYPES = {
     "ppx_cuda_version": (C.c_char_p, []),

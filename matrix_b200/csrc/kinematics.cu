@@ -271,9 +271,10 @@ __global__ void __launch_bounds__(128, PPX_IK_MINB)
             for (int i = 0; i < NJ; i++)
                 qi[i] = qn[i];
             it++;
-            const double ew = sqrt(fma(vs[2], vs[2], fma(vs[1], vs[1], vs[0] * vs[0])));
-            const double ev = sqrt(fma(vs[5], vs[5], fma(vs[4], vs[4], vs[3] * vs[3])));
-            conv = ew < EPS_SP && ev < EPS_SP;
+            // |Vs.w| < EPS_SP and |Vs.v| < EPS_SP (lie_test.cpp:103), compared as squares
+            const double ew2 = fma(vs[2], vs[2], fma(vs[1], vs[1], vs[0] * vs[0]));
+            const double ev2 = fma(vs[5], vs[5], fma(vs[4], vs[4], vs[3] * vs[3]));
+            conv = ew2 < EPS_SP * EPS_SP && ev2 < EPS_SP * EPS_SP;
             finished = conv || it >= a.max_iter;
         }
         if (busy && finished)

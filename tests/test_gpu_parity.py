@@ -935,3 +935,34 @@ def test_bench_prints_the_contract_line(mb):
     assert abs(d["value"] - 1048576 * 4 / (d["ms_per_step"] * 4e-3)) < 1e-6 * d["value"]
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 1048576 * 48 and e["d2h_bytes_per_step"] == 1048576 * 416 and 0 < e["value"] < d["value"]
+
+
+def test_host_abi_is_thread_safe_and_keeps_its_scratch(mb, port):
+    """Concurrent host-ABI calls from several threads (the streams and the scratch pool are shared, per device) give
+    the results of serial calls; ppx_cuda_host_trim() hands the retained scratch back."""
+    import threading
+    from matrix_b200 import _lib, host
+    S, M = synth.UR5_SCREWS, synth.UR5_HOME
+    kin = host.Kinematics(S, M)
+    qs = [synth.joint_angles(20000 + 977 * k, seed=0xF0 + k) for k in range(6)]
+    ref = [port.poe_fk_jacobian(S, M, q) for q in qs]
+    got, errs = [None] * len(qs), []
+
+    def work(k):
+        try:
+            for _ in range(5):
+                got[k] = kin.fk_jacobian(qs[k])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(qs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs
+    for (T, Js), (rT, rJs) in zip(got, ref):
+        assert rel_err(T, rT).max() < REL and rel_err(Js, rJs).max() < REL
+    assert _lib.lib.ppx_cuda_host_trim() == 0
+    T, Js = kin.fk_jacobian(qs[0])  # still works after the trim
+    assert rel_err(T, ref[0][0]).max() < REL
