@@ -42,7 +42,10 @@ struct OpLinsolveQR
 template <int M, int N, bool WANT_U, bool WANT_V>
 struct OpSVD
 {
-    static constexpr int BLOCK = 128, MINB = (M * N >= 36 ? 2 : 4), MAXW = (M * N > N * N ? M * N : N * N);
+#ifndef PPX_SVD_MINB
+#define PPX_SVD_MINB 2
+#endif
+    static constexpr int BLOCK = 128, MINB = (M * N >= 36 ? PPX_SVD_MINB : 4), MAXW = (M * N > N * N ? M * N : N * N);
     const double *A;
     double *U;
     double *w;
