@@ -749,6 +749,42 @@ def test_full_size_32M_ik_newton_step(mb):
     assert float(e1.median()) < 0.05 * float(e0.median())
 
 
+def test_full_size_inverse_space_and_newton_loop(mb):
+    """SURVEY 8(f) rows 1 and 4 at bench size: kinematics<6>::inverseSpace on 2^24 targets and the Newton loop on 2^22,
+    checked through what the solvers promise -- every instance reported solved reproduces its target pose, the answer
+    stays inside the joint ranges, counts and status codes are in range -- all on the device."""
+    w = _soa_workload("inverse_space_codo")
+    q, st, fn = w.out
+    assert bool(torch.isfinite(q).all()) and bool(((st == mb.CONVERGED) | (st == mb.DIVERGED)).all())
+    solved = (st == mb.CONVERGED) & (fn <= 0.5 * 1.1920928955078125e-07)
+    assert float(solved.double().mean()) > 0.99
+    assert bool((q.abs() <= np.pi).all())  # the box of the demo, robotics.hpp:126-152 with joint ranges (-pi, pi)
+    T = w.kin.forwardSpace(q)
+    assert float((T - w.Tt)[solved].abs().max()) < 5e-7
+    # instances that are not CONVERGED return the start (robotics.hpp:151)
+    div = st == mb.DIVERGED
+    if bool(div.any()):
+        assert bool((q[div] == w.q0[div]).all())
+    del w
+    torch.cuda.empty_cache()
+    n = 1 << 22
+    kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
+    qi = torch.empty((n, 6), dtype=torch.float64, device="cuda")
+    mb.fill_uniform(qi, synth.SEEDS["ik_newton_step"], 0, -np.pi, np.pi)
+    d = torch.empty_like(qi)
+    mb.fill_uniform(d, synth.SEEDS["ik_newton_step"] ^ 0xA5A5, 0, -0.05, 0.05)
+    Tt = kin.forwardSpace(qi + d)
+    qs, it, st = kin.inverseSpaceNewton(Tt, qi, 20)
+    assert bool(((it >= 1) & (it <= 20)).all()) and bool(((st == mb.CONVERGED) | (st == mb.DIVERGED)).all())
+    conv = st == mb.CONVERGED
+    assert float(conv.double().mean()) > 0.99 and bool((it[~conv] == 20).all())
+    # the loop stops on the residual BEFORE its last update (lie_test.cpp:103-110): the pose after it is off by the
+    # square of that update, i.e. by ~(kappa * 1.2e-7)^2 -- inside the tolerance except next to a singularity
+    err = (kin.forwardSpace(qs) - Tt).abs().amax(dim=1)[conv]
+    assert float(err.kthvalue(int(0.999 * err.numel())).values) < 1.1920928955078125e-07 and float(err.max()) < 1e-3
+    assert 3.5 < float(it.double().mean()) < 5.0
+
+
 # --------------------------------------------------------------------------------------- out-of-bounds canaries
 @pytest.mark.parametrize("n", [1, 31, 33, 255, 257, 1000])
 def test_persistent_and_staged_kernels_stay_inside_their_buffers(mb, port, n):
