@@ -7,39 +7,7 @@
 // compiled by tests/test_codo_host.py into a scratch .so next to the test.
 //
 //   g++ -O2 -std=c++17 -shared -fPIC -ffp-contract=off -Wno-unknown-pragmas tests/cpp/codo_host.cpp -o codo_host.so
-#include <cmath>
-#include <cstddef>
-#include <cstdint>
-#include <cstring>
-
-// the CUDA spellings ppx_math.cuh uses outside templates
-#define __device__
-#define __host__
-#define __forceinline__ inline __attribute__((always_inline))
-#define __noinline__ __attribute__((noinline))
-static inline int __double2hiint(double x)
-{
-    int64_t u;
-    std::memcpy(&u, &x, 8);
-    return (int)(u >> 32);
-}
-static inline int __double2loint(double x)
-{
-    int64_t u;
-    std::memcpy(&u, &x, 8);
-    return (int)(u & 0xffffffff);
-}
-static inline double __hiloint2double(int hi, int lo)
-{
-    const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
-    double x;
-    std::memcpy(&x, &u, 8);
-    return x;
-}
-static inline int __any_sync(unsigned, int p) { return p; }
-static inline int __all_sync(unsigned, int p) { return p; }
-static inline int max(int a, int b) { return a > b ? a : b; }
-static inline int min(int a, int b) { return a < b ? a : b; }
+#include "cuda_host_shims.h"
 
 #include "../../matrix_b200/csrc/ppx_codo.cuh"
 
