@@ -110,4 +110,74 @@ int mh_square_pinv_solve6(const double *A, const double *b, double *x, int allow
     return 0;
 }
 
+// ---- Lie maps and kinematics (ppx_math.cuh: se3_exp, SE3_log, so3_exp, SO3_log, poe_fk_jacobian) ----
+int mh_se3_exp(const double *xi, double *T, size_t n)
+{
+    for (size_t i = 0; i < n; i++)
+    {
+        double x[6], m[16];
+        std::memcpy(x, xi + 6 * i, sizeof(x));
+        Rigid t;
+        se3_exp(x, t);
+        rigid_to_record(t, m);
+        std::memcpy(T + 16 * i, m, sizeof(m));
+    }
+    return 0;
+}
+int mh_SE3_log(const double *T, double *xi, size_t n)
+{
+    for (size_t i = 0; i < n; i++)
+    {
+        double x[6], m[16];
+        std::memcpy(m, T + 16 * i, sizeof(m));
+        Rigid t;
+        rigid_from_record(m, t);
+        SE3_log(t, x);
+        std::memcpy(xi + 6 * i, x, sizeof(x));
+    }
+    return 0;
+}
+int mh_so3_exp(const double *w, double *R, size_t n)
+{
+    for (size_t i = 0; i < n; i++)
+    {
+        double x[3], r[9];
+        std::memcpy(x, w + 3 * i, sizeof(x));
+        so3_exp(x, r);
+        std::memcpy(R + 9 * i, r, sizeof(r));
+    }
+    return 0;
+}
+int mh_SO3_log(const double *R, double *w, size_t n)
+{
+    for (size_t i = 0; i < n; i++)
+    {
+        double x[3], r[9];
+        std::memcpy(r, R + 9 * i, sizeof(r));
+        SO3_log(r, x);
+        std::memcpy(w + 3 * i, x, sizeof(x));
+    }
+    return 0;
+}
+// 6-joint chain: T (16) and Js (36) per instance
+int mh_fk_jacobian6(const double *screws, const double *home, const double *q, double *T, double *Js, size_t n)
+{
+    ChainConst<6> ch;
+    fold_chain<6>(screws, home, ch);
+    for (size_t i = 0; i < n; i++)
+    {
+        double qi[6], m[16], js[36];
+        std::memcpy(qi, q + 6 * i, sizeof(qi));
+        Rigid t;
+        poe_fk_jacobian<6, true, true>(ch, qi, t, [&](int col, const double(&v)[6]) {
+            for (int k = 0; k < 6; k++)
+                js[6 * col + k] = v[k];
+        });
+        rigid_to_record(t, m);
+        std::memcpy(T + 16 * i, m, sizeof(m));
+        std::memcpy(Js + 36 * i, js, sizeof(js));
+    }
+    return 0;
+}
+
 } // extern "C"

@@ -143,3 +143,38 @@ def test_square_pinv_solve_paths_on_the_host(mh, port, fixtures):
         assert np.all(errd < 1e-6)
     well = kappa < 1e3
     assert np.abs(out[1][well] - out[0][well]).max() < 1e-11
+
+
+def test_device_lie_maps_and_kinematics_on_the_host(mh, port, fixtures):
+    """se3::exp, SE3::log, so3::exp, SO3::log and the UR5 forward kinematics + Jacobian as the kernels compute them
+    (closed forms, branch-free reciprocals) against the oracle at the 1e-12 bar, incl. the recorded edge cases
+    (theta = 0, 1e-9 ... pi) of the reference itself."""
+    xi = np.ascontiguousarray(np.vstack([synth.se3_twists(N), fixtures["se3_exp.xi"]]))
+    n = xi.shape[0]
+    T, back = np.empty((n, 16)), np.empty((n, 6))
+    assert mh.mh_se3_exp(_p(xi), _p(T), C.c_size_t(n)) == 0
+    rT = port.se3_exp(xi)
+    assert np.abs(T - rT).max() < 1e-14
+    assert mh.mh_SE3_log(_p(np.ascontiguousarray(rT)), _p(back), C.c_size_t(n)) == 0
+    rback = port.SE3_log(rT)
+    # theta = acos(c) carries the rounding of c divided by sin(theta): 1e-12 everywhere except next to theta = pi
+    theta = np.linalg.norm(xi[:, :3], axis=1)
+    tol = 1e-12 + 4 * np.finfo(float).eps / np.maximum(np.abs(np.sin(theta)), 1e-9)
+    assert np.all(np.abs(back - rback).max(axis=1) <= tol * np.maximum(1.0, np.abs(rback).max(axis=1)))
+    w = np.ascontiguousarray(xi[:, :3])
+    R, wb = np.empty((n, 9)), np.empty((n, 3))
+    assert mh.mh_so3_exp(_p(w), _p(R), C.c_size_t(n)) == 0
+    assert np.abs(R - port.so3_exp(w)).max() < 1e-14
+    Rm = np.ascontiguousarray(fixtures["SO3_log.R"])
+    wl = np.empty((Rm.shape[0], 3))
+    assert mh.mh_SO3_log(_p(Rm), _p(wl), C.c_size_t(Rm.shape[0])) == 0
+    ref = fixtures["SO3_log.w"]
+    assert np.all(np.abs(wl - ref).max(axis=1) <= 1e-9)  # near theta = pi the log is ill-conditioned: 1e-16 / sin(theta)
+    gen = np.linalg.norm(ref, axis=1) < 3.0
+    assert np.abs(wl[gen] - ref[gen]).max() < 1e-12
+    q = np.ascontiguousarray(fixtures["ur5.q"])
+    S = np.ascontiguousarray(synth.UR5_SCREWS, dtype=np.float64)
+    M = np.ascontiguousarray(synth.UR5_HOME, dtype=np.float64)
+    Tq, Js = np.empty((q.shape[0], 16)), np.empty((q.shape[0], 36))
+    assert mh.mh_fk_jacobian6(_p(S), _p(M), _p(q), _p(Tq), _p(Js), C.c_size_t(q.shape[0])) == 0
+    assert np.abs(Tq - fixtures["ur5.T"]).max() < 1e-14 and np.abs(Js - fixtures["ur5.Js"]).max() < 1e-14
