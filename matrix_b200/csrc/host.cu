@@ -54,7 +54,6 @@ inline size_t env_chunk_bytes()
 // per-device resources kept between calls
 struct DevCtx
 {
-    cudaMemPool_t pool = nullptr;
     std::vector<cudaStream_t> idle; // streams not in use by a call
 };
 std::mutex g_host_mu;
@@ -68,24 +67,11 @@ int host_acquire(int want, cudaStream_t *st, cudaMemPool_t &pool, int &device)
         return (int)e;
     if (device < 0 || device >= 64)
         return PPX_ERR_NO_DEVICE;
+    const int prc = ppx_scratch_pool(device, &pool);
+    if (prc != PPX_OK)
+        return prc;
     std::lock_guard<std::mutex> lock(g_host_mu);
     DevCtx &c = g_host_ctx[device];
-    if (c.pool == nullptr)
-    {
-        cudaMemPoolProps props = {};
-        props.allocType = cudaMemAllocationTypePinned;
-        props.handleTypes = cudaMemHandleTypeNone;
-        props.location.type = cudaMemLocationTypeDevice;
-        props.location.id = device;
-        e = cudaMemPoolCreate(&c.pool, &props);
-        if (e != cudaSuccess)
-            return (int)e;
-        const char *env = std::getenv("PPX_HOST_POOL_MIB");
-        const long mib = env ? std::atol(env) : 1024;
-        unsigned long long keep = (unsigned long long)(mib < 0 ? 0 : mib) << 20;
-        cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    pool = c.pool;
     for (int s = 0; s < want; s++)
     {
         if (!c.idle.empty())
@@ -203,18 +189,7 @@ typedef double *md;
 extern "C"
 {
 
-int ppx_cuda_host_trim(void)
-{
-    std::lock_guard<std::mutex> lock(g_host_mu);
-    for (DevCtx &c : g_host_ctx)
-        if (c.pool != nullptr)
-        {
-            cudaError_t e = cudaMemPoolTrimTo(c.pool, 0);
-            if (e != cudaSuccess)
-                return (int)e;
-        }
-    return PPX_OK;
-}
+int ppx_cuda_host_trim(void) { return ppx_scratch_trim(); }
 
 int ppx_cuda_host_so3_exp(const double *w, double *R, size_t n)
 {

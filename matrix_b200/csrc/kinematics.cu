@@ -401,35 +401,44 @@ int ik_step_n(const double *screws, const double *home, const double *q, const d
 }
 
 // Launch of a persistent kernel with a work counter: as many CTAs as are resident at once; the counter lives for this
-// launch only (stream-ordered allocation, zeroed on the stream).
-template <class Kernel, class Args>
-int launch_persistent(Kernel kern, int block, size_t smem, const Args &a, size_t n, size_t ld, void *stream)
+// launch only (stream-ordered allocation from the library's retained pool, zeroed on the stream).
+template <auto Kern, class Args>
+int launch_persistent(int block, size_t smem, const Args &a, size_t n, size_t ld, void *stream)
 {
     DeviceInfo info;
     int device = 0;
     int rc = device_info(info, device);
     if (rc != PPX_OK)
         return rc;
+    static std::atomic<int> blocks_per_sm[64]; // per instantiation (= per kernel), per device; 0 = not asked yet
+    int per_sm = blocks_per_sm[device].load(std::memory_order_relaxed);
+    if (per_sm == 0)
+    {
+        if (smem > 48 * 1024)
+        {
+            cudaError_t e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess)
+                return (int)e;
+        }
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, Kern, block, smem);
+        if (e != cudaSuccess)
+            return (int)e;
+        per_sm = per_sm > 0 ? per_sm : 1;
+        blocks_per_sm[device].store(per_sm, std::memory_order_relaxed);
+    }
+    cudaMemPool_t pool = nullptr;
+    rc = ppx_scratch_pool(device, &pool);
+    if (rc != PPX_OK)
+        return rc;
     cudaStream_t s = (cudaStream_t)stream;
     unsigned long long *next = nullptr;
-    cudaError_t e = cudaMallocAsync((void **)&next, sizeof(*next), s);
+    cudaError_t e = cudaMallocFromPoolAsync((void **)&next, sizeof(*next), pool, s);
     if (e != cudaSuccess)
         return (int)e;
     cudaMemsetAsync(next, 0, sizeof(*next), s);
-    if (smem > 48 * 1024)
-    {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess)
-        {
-            cudaFreeAsync(next, s);
-            return (int)e;
-        }
-    }
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem);
     const size_t want = (n + block - 1) / block;
-    const size_t cap = (size_t)info.sms * (per_sm > 0 ? per_sm : 1);
-    kern<<<(unsigned)(want < cap ? want : cap), block, smem, s>>>(a, n, ld, next);
+    const size_t cap = (size_t)info.sms * per_sm;
+    Kern<<<(unsigned)(want < cap ? want : cap), block, smem, s>>>(a, n, ld, next);
     g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);
     e = cudaPeekAtLastError();
     cudaFreeAsync(next, s);
@@ -504,8 +513,8 @@ int ppx_cuda_batch_ik_solve(const double *screws, const double *home, int njoint
     fold_chain<6>(screws, home, a.ch);
     a.q0 = q0, a.Tt = Ttarget, a.q_out = q_out, a.iters = iters, a.status = status, a.max_iter = max_iter;
     a.allow_lu = g_ppx_square_lu.load(std::memory_order_relaxed) != 0;
-    return layout == PPX_LAYOUT_AOS ? launch_persistent(ik_solve_kernel<LAYOUT_AOS>, 128, 0, a, n, ld, stream)
-                                    : launch_persistent(ik_solve_kernel<LAYOUT_SOA>, 128, 0, a, n, ld, stream);
+    return layout == PPX_LAYOUT_AOS ? launch_persistent<ik_solve_kernel<LAYOUT_AOS>>(128, 0, a, n, ld, stream)
+                                    : launch_persistent<ik_solve_kernel<LAYOUT_SOA>>(128, 0, a, n, ld, stream);
 }
 
 int ppx_cuda_batch_ik_codo(const double *screws, const double *home, int njoints, const double *lo, const double *hi,
@@ -529,8 +538,8 @@ int ppx_cuda_batch_ik_codo(const double *screws, const double *home, int njoints
         a.hi[i] = hi[i];
     }
     a.Tt = Ttarget, a.init = init, a.q_out = q_out, a.x_raw = x_raw, a.fnorm = fnorm, a.status = status;
-    return layout == PPX_LAYOUT_AOS ? launch_persistent(ik_codo_kernel<LAYOUT_AOS>, PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream)
-                                    : launch_persistent(ik_codo_kernel<LAYOUT_SOA>, PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream);
+    return layout == PPX_LAYOUT_AOS ? launch_persistent<ik_codo_kernel<LAYOUT_AOS>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream)
+                                    : launch_persistent<ik_codo_kernel<LAYOUT_SOA>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream);
 }
 
 } // extern "C"

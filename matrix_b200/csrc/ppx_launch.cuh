@@ -17,6 +17,8 @@
 
 extern std::atomic<uint64_t> g_ppx_launch_count; // util.cu
 extern std::atomic<int> g_ppx_square_lu;         // util.cu: ppx_cuda_set_square_solve_lu
+int ppx_scratch_pool(int device, cudaMemPool_t *pool); // util.cu: the library's retained scratch pool of a device
+int ppx_scratch_trim();                                // util.cu: give the retained scratch back to the driver
 
 #define PPX_CHECK_PTRS(...)                          \
     do                                               \

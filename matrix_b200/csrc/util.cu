@@ -1,12 +1,62 @@
 // util.cu -- device/memory helpers behind the C ABI, layout conversion, the counter-based input
 // generator and the fp64 peak probe.  None of this is on the timed hot path.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "ppx_launch.cuh"
 
 std::atomic<uint64_t> g_ppx_launch_count{0};
 std::atomic<int> g_ppx_square_lu{1};
+
+// One memory pool per device for the library's own short-lived device scratch (host-ABI staging buffers, the work
+// counters of the persistent kernels).  Unlike the default pool it keeps up to PPX_HOST_POOL_MIB (default 1024) MiB of
+// freed memory mapped, so that a call does not pay for mapping device memory again.
+namespace
+{
+std::mutex g_pool_mu;
+cudaMemPool_t g_pools[64] = {};
+} // namespace
+
+int ppx_scratch_pool(int device, cudaMemPool_t *pool)
+{
+    if (device < 0 || device >= 64)
+        return PPX_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    if (g_pools[device] == nullptr)
+    {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaError_t e = cudaMemPoolCreate(&g_pools[device], &props);
+        if (e != cudaSuccess)
+        {
+            g_pools[device] = nullptr;
+            return (int)e;
+        }
+        const char *env = std::getenv("PPX_HOST_POOL_MIB");
+        const long mib = env ? std::atol(env) : 1024;
+        unsigned long long keep = (unsigned long long)(mib < 0 ? 0 : mib) << 20;
+        cudaMemPoolSetAttribute(g_pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    *pool = g_pools[device];
+    return PPX_OK;
+}
+int ppx_scratch_trim()
+{
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (cudaMemPool_t p : g_pools)
+        if (p != nullptr)
+        {
+            cudaError_t e = cudaMemPoolTrimTo(p, 0);
+            if (e != cudaSuccess)
+                return (int)e;
+        }
+    return PPX_OK;
+}
 
 namespace
 {
