@@ -350,8 +350,11 @@ def main():
         w.host_step()  # warm-up (page-locks, stream-ordered pool growth)
         barrier()
         t0 = time.perf_counter()
+        e2e_steps_ms = []
         for _ in range(args.e2e_steps):
-            loss = w.host_step()
+            ts = time.perf_counter()
+            loss = w.host_step()  # blocking: returns when the outputs are in host memory
+            e2e_steps_ms.append((time.perf_counter() - ts) * 1e3)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -363,6 +366,7 @@ def main():
                "pcie_gbs": (h2d + d2h) * args.e2e_steps / dt / 1e9, "pcie_h2d_gbs_measured": pcie["h2d"],
                "pcie_d2h_gbs_measured": pcie["d2h"], "result_probe": loss}
         e2e["numa_bound"] = bool(near)
+        e2e["step_ms"] = {"min": min(e2e_steps_ms), "median": statistics.median(e2e_steps_ms), "max": max(e2e_steps_ms)}
         os.sched_setaffinity(0, all_cpus)
         for k in ("hq", "hT", "hJ"):
             if hasattr(w, k):
