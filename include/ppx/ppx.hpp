@@ -8,10 +8,10 @@
 //
 // What lives where
 //   - Containers (Matrix<M,N>: column-major doubles, sizeof == M*N*8, list constructors that truncate /
-//     zero-pad like the reference's, element access, transpose, +, -, scalar and matrix products, ==) are
-//     plain host code: they carry data, they are not the hot path.
-//   - Every hot-path ROUTINE (exp, log, Adt, I, SE3 product, linsolve, SVD, EigenValue, forwardSpace,
-//     jacobiSpace, inverseSpace) runs on the GPU.  The batch_* functions take host arrays of reference
+//     zero-pad like the reference's, element access, transpose, +, -, scalar products, ==) are plain host
+//     code: they carry data, they are not the hot path.
+//   - Every hot-path ROUTINE (matrix product, exp, log, Adt, I, SE3 product, linsolve, SVD, EigenValue,
+//     forwardSpace, jacobiSpace, inverseSpace) runs on the GPU.  The batch_* functions take host arrays of reference
 //     records -- std::vector<ppx::Matrix<M,N>>::data() -- and call the ppx_cuda_host_* entry points, which
 //     overlap H2D / kernel / D2H.  The single-value members (xi.exp(), T.log(), linsolve<>(A, b), ...)
 //     exist for source compatibility and are batches of one: there is no CPU implementation of the math
@@ -128,14 +128,14 @@ public:
             r(i, i) = m_[i];
         return r;
     }
+    // MatrixS::operator*, include/matrixs.hpp:596-640: a batch of one through ppx_cuda_host_matmul (k-j-i
+    // accumulation, products and sums rounded separately like the reference's loop); dimensions up to 8
     template <std::size_t L>
-    Matrix<M, L> operator*(const Matrix<N, L> &o) const // include/matrixs.hpp:596-640 (k-j-i accumulation)
+    Matrix<M, L> operator*(const Matrix<N, L> &o) const
     {
+        static_assert(M <= 8 && N <= 8 && L <= 8, "libppx_cuda multiplies matrices with dimensions up to 8");
         Matrix<M, L> r;
-        for (std::size_t k = 0; k < N; k++)
-            for (std::size_t j = 0; j < L; j++)
-                for (std::size_t i = 0; i < M; i++)
-                    r[i + j * M] += m_[i + k * M] * o[k + j * N];
+        cuda::check(ppx_cuda_host_matmul((int)M, (int)N, (int)L, data(), o.data(), r.data(), 1));
         return r;
     }
     Matrix operator+(const Matrix &o) const { return zip(o, [](double a, double b) { return a + b; }); }
@@ -261,6 +261,14 @@ public:
     SO3(const Matrix<3, 3> &o) : Matrix<3, 3>(o) {}
     template <typename T, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type>
     SO3(std::initializer_list<T> l) : Matrix<3, 3>(l) {}
+    SO3(const Matrix<3, 1> &xAxis, const Matrix<3, 1> &yAxis, const Matrix<3, 1> &zAxis) // :41-42: the axes are the columns
+        : Matrix<3, 3>{xAxis[0], xAxis[1], xAxis[2], yAxis[0], yAxis[1], yAxis[2], zAxis[0], zAxis[1], zAxis[2]}
+    {
+    }
+    SO3(double m[3][3]) // :43: row-major C array
+        : Matrix<3, 3>{m[0][0], m[1][0], m[2][0], m[0][1], m[1][1], m[2][1], m[0][2], m[1][2], m[2][2]}
+    {
+    }
     using Matrix<3, 3>::operator*;
     SO3 operator*(const SO3 &o) const { return SO3(Matrix<3, 3>::operator*(o)); }
     Matrix<3, 3> Adt() const { return *this; }
@@ -291,6 +299,11 @@ public:
                 (*this)(r, c) = R(r, c);
         for (int r = 0; r < 3; r++)
             (*this)(r, 3) = p[r];
+    }
+    SE3(double m[4][4]) // :200: row-major C array; the bottom row is set to (0, 0, 0, 1) whatever m holds
+        : Matrix<4, 4>{m[0][0], m[1][0], m[2][0], 0.0, m[0][1], m[1][1], m[2][1], 0.0,
+                       m[0][2], m[1][2], m[2][2], 0.0, m[0][3], m[1][3], m[2][3], 1.0}
+    {
     }
     using Matrix<4, 4>::operator*;
     SO3 Rot() const { return SO3(sub<3, 3>(0, 0)); }
@@ -660,6 +673,18 @@ inline void batch_log(const SE3 *T, se3 *xi, std::size_t n) { check(ppx_cuda_hos
 // xi[i].exp().log() without materialising the SE3 (BASELINE config 1)
 inline void batch_exp_log(const se3 *xi, se3 *out, std::size_t n) { check(ppx_cuda_host_se3_exp_log(dp(xi), dp(out), n)); }
 inline void batch_mul(const SE3 *A, const SE3 *B, SE3 *C, std::size_t n) { check(ppx_cuda_host_SE3_mul(dp(A), dp(B), dp(C), n)); }
+// MatrixS<M,N>::operator* over n pairs (include/matrixs.hpp:596-640), C[i] = A[i] * B[i]
+template <std::size_t M, std::size_t N, std::size_t L>
+void batch_mul(const Matrix<M, N> *A, const Matrix<N, L> *B, Matrix<M, L> *C, std::size_t n)
+{
+    static_assert(M <= 8 && N <= 8 && L <= 8, "libppx_cuda multiplies matrices with dimensions up to 8");
+    check(ppx_cuda_host_matmul((int)M, (int)N, (int)L, dp(A), dp(B), dp(C), n));
+}
+// the devices the batch_* calls spread their instances over: use_devices({0, 1, 2, 3}), use_all_devices(), or
+// use_current_device() (the default unless PPX_CUDA_DEVICES is set); see ppx_cuda_host_set_devices
+inline void use_devices(const std::vector<int> &devices) { check(ppx_cuda_host_set_devices(devices.data(), (int)devices.size())); }
+inline void use_all_devices() { check(ppx_cuda_host_set_devices(nullptr, -1)); }
+inline void use_current_device() { check(ppx_cuda_host_set_devices(nullptr, 0)); }
 inline void batch_I(const SE3 *T, SE3 *Ti, std::size_t n) { check(ppx_cuda_host_SE3_inv(dp(T), dp(Ti), n)); }
 inline void batch_Adt(const SE3 *T, Matrix<6, 6> *Ad, std::size_t n) { check(ppx_cuda_host_SE3_Adt(dp(T), dp(Ad), n)); }
 inline void batch_adt(const se3 *xi, Matrix<6, 6> *ad, std::size_t n) { check(ppx_cuda_host_se3_adt(dp(xi), dp(ad), n)); }

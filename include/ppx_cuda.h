@@ -20,8 +20,11 @@
  *                      stride in doubles (`ld` is ignored for AOS).  This is the fast layout.
  *    Every array of one call uses the same layout and the same ld.
  *  - Work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = default stream) of
- *    the CURRENT device; calls are asynchronous, never synchronise, keep no global state and
- *    may be issued concurrently from several host threads / devices.
+ *    the CURRENT device; calls are asynchronous, never synchronise and may be issued concurrently
+ *    from several host threads / devices.  The compute entry points keep no state between calls.
+ *    The only process-wide settings are the two configuration knobs declared below
+ *    (ppx_cuda_set_square_solve_lu, a measurement switch, and ppx_cuda_host_set_devices, the device
+ *    list of the host-buffer face) and the library's caches (occupancy, streams, scratch pool).
  *  - Return value: PPX_OK (0), a PPX_ERR_* code (< 0), or a positive cudaError_t from the
  *    launch.  ppx_cuda_error_string() explains either.
  *  - Per-instance numerical status uses ppx::StatusCode's enumerator order
@@ -61,17 +64,21 @@ int ppx_cuda_device_count(void);
 int ppx_cuda_set_device(int device);
 int ppx_cuda_malloc(void **dptr, size_t bytes);
 int ppx_cuda_free(void *dptr);
-int ppx_cuda_malloc_host(void **hptr, size_t bytes);       /* pinned host memory */
+/* pinned host memory, usable by every device of the process.  Blocks >= 64 MiB are mapped with transparent huge pages
+ * (PPX_HOST_HUGEPAGES=0: off), faulted in by several threads and page-locked with one cudaHostRegister; smaller ones
+ * come from cudaHostAlloc (PPX_HOST_ALLOC=cuda: always). */
+int ppx_cuda_malloc_host(void **hptr, size_t bytes);
 int ppx_cuda_free_host(void *hptr);
 int ppx_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int ppx_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
 int ppx_cuda_stream_synchronize(void *stream);
 /* number of kernel launches this library has issued in this process (all threads) */
 uint64_t ppx_cuda_launch_count(void);
-/* Square linsolve<SVD> systems (ppx_cuda_batch_linsolve_svd with m == n, the Newton step of ik_newton_step / ik_solve)
- * are solved by LU with partial pivoting whenever every pivot is above 1e-8 of the largest -- the same A^+ b to the same
- * accuracy, the truncation of SVD::solve (linalg.hpp:889-901) only acts beyond cond ~ 2e15 -- and by the Jacobi SVD
- * otherwise.  enable = 0 forces the Jacobi SVD solve everywhere (to measure it); returns the previous setting.
+/* Square linsolve<SVD> systems (ppx_cuda_batch_linsolve_svd with m == n, the Newton step of ik_newton_step / ik_solve,
+ * square pinv) are solved by LU with partial pivoting whenever a RIGOROUS upper bound of cond_inf(A), computed from the
+ * factors (|A|_inf |M(U)^-1 e|_inf |M(L)^-1 e|_inf, M = comparison matrix), is below 1e10 -- the truncation of SVD::solve
+ * (linalg.hpp:889-901) only acts beyond cond ~ 2e15, so A^+ b = A^-1 b there -- and by the Jacobi SVD otherwise.
+ * enable = 0 forces the Jacobi SVD solve everywhere (a measurement switch); returns the previous setting.
  * Process-wide, read at launch time. */
 int ppx_cuda_set_square_solve_lu(int enable);
 
@@ -88,6 +95,13 @@ int ppx_cuda_fp64_peak_probe(double *tflops, void *stream);
 /* measurement helper: writes `planes` SoA component planes of n doubles (mode 0: 64-bit stores, one instance per
  * thread, the pattern of the batch kernels; mode 1: 128-bit stores, two instances per thread) */
 int ppx_cuda_probe_write(double *out, int planes, size_t n, size_t ld, int mode, void *stream);
+
+/* ---- MatrixS<M,N>::operator*, include/matrixs.hpp:596-640 ------------------------------------ */
+/* C (m x l) = A (m x n) B (n x l), zero-initialised, accumulated in the reference's k-j-i order with separately
+ * rounded products and sums (no FMA): bit-identical to the reference compiled without contraction.  Unrolled kernels
+ * for (3,3,3) (4,4,4) (6,6,6) (6,6,1) (4,4,1) (3,3,1); every other shape with m, n, l <= 8 runs a generic kernel. */
+int ppx_cuda_batch_matmul(int m, int n, int l, const double *A, const double *B, double *C, size_t count, int layout,
+                          size_t ld, void *stream);
 
 /* ---- Lie group / algebra ------------------------------------------------------------------- */
 /* so3::exp, include/liegroup.hpp:116-133.  w: 3 -> R: 9 */
@@ -178,6 +192,18 @@ int ppx_cuda_batch_norm2(int m, int n, const double *A, double *s, size_t count,
  * between calls, which is what makes small calls cheap; ppx_cuda_host_trim() returns the scratch to the driver.
  * Thread-safe.  Optional outputs (T/Js, Vs, iters, status, U, V, z) may be NULL exactly as in the device entry points. */
 int ppx_cuda_host_trim(void);
+/* Devices the ppx_cuda_host_* calls spread a batch over (the path shards by instance index, no exchange
+ * step).  count > 0: exactly these device ordinals; count < 0: every visible device; count == 0: the calling thread's
+ * current device only, which is also the default unless the environment variable PPX_CUDA_DEVICES ("all" or
+ * "0,1,2,...") says otherwise.  With several devices a call runs one worker thread per device and hands chunks of the
+ * batch out from one shared queue, so the result is bitwise the one-device result whatever the split.  Process-wide. */
+int ppx_cuda_host_set_devices(const int *devices, int count);
+/* -> number of configured devices (0 = current device only); the first `capacity` ordinals are written to devices */
+int ppx_cuda_host_get_devices(int *devices, int capacity);
+/* measurement helper: all configured devices copy at once through `host` (bytes, pinned) for `seconds`;
+ * direction 0 H2D, 1 D2H, 2 both.  gbs[i] = GB/s device i sustained meanwhile: the ceiling of any host-buffer path. */
+int ppx_cuda_host_copy_probe(void *host, size_t bytes, int direction, double seconds, double *gbs);
+int ppx_cuda_host_matmul(int m, int n, int l, const double *A, const double *B, double *C, size_t count);
 int ppx_cuda_host_so3_exp(const double *w, double *R, size_t n);
 int ppx_cuda_host_SO3_log(const double *R, double *w, size_t n);
 int ppx_cuda_host_se3_exp(const double *xi, double *T, size_t n);

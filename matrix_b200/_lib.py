@@ -42,6 +42,7 @@ _SIGNATURES = {
     "ppx_cuda_fill_uniform": [_vp, _sz, _u64, _u64, _d, _d, _vp],
     "ppx_cuda_fp64_peak_probe": [C.POINTER(_d), _vp],
     "ppx_cuda_probe_write": [_vp, _i, _sz, _sz, _i, _vp],
+    "ppx_cuda_batch_matmul": [_i, _i, _i, _vp, _vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_batch_so3_exp": [_vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_batch_SO3_log": [_vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_batch_se3_exp": [_vp, _vp, _sz, _i, _sz, _vp],
@@ -65,6 +66,7 @@ _SIGNATURES = {
     "ppx_cuda_batch_det": [_i, _vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_batch_pinv": [_i, _i, _vp, _vp, _sz, _i, _sz, _vp],
     "ppx_cuda_batch_norm2": [_i, _i, _vp, _vp, _sz, _i, _sz, _vp],
+    "ppx_cuda_host_matmul": [_i, _i, _i, _vp, _vp, _vp, _sz],
     "ppx_cuda_host_so3_exp": [_vp, _vp, _sz],
     "ppx_cuda_host_SO3_log": [_vp, _vp, _sz],
     "ppx_cuda_host_se3_exp": [_vp, _vp, _sz],
@@ -89,6 +91,9 @@ _SIGNATURES = {
     "ppx_cuda_host_pinv": [_i, _i, _vp, _vp, _sz],
     "ppx_cuda_host_norm2": [_i, _i, _vp, _vp, _sz],
     "ppx_cuda_host_trim": [],
+    "ppx_cuda_host_set_devices": [C.POINTER(C.c_int), _i],
+    "ppx_cuda_host_get_devices": [C.POINTER(C.c_int), _i],
+    "ppx_cuda_host_copy_probe": [_vp, _sz, _i, _d, C.POINTER(_d)],
 }
 _RESTYPES = {
     "ppx_cuda_version": (C.c_char_p, []),

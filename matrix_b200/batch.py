@@ -38,12 +38,17 @@ def _in(t, width, layout, n=None):
     if layout == AOS:
         if t.shape[1] != width:
             raise ValueError(f"AOS batch must have shape (n, {width}), got {tuple(t.shape)}")
-        return C.c_void_p(t.data_ptr()), t.shape[0] if n is None else n, 0
-    if layout == SOA:
+        rows, ld = t.shape[0], 0
+    elif layout == SOA:
         if t.shape[0] != width:
             raise ValueError(f"SOA batch must have shape ({width}, ld), got {tuple(t.shape)}")
-        return C.c_void_p(t.data_ptr()), t.shape[1] if n is None else n, t.shape[1]
-    raise ValueError("layout must be AOS or SOA")
+        rows, ld = t.shape[1], t.shape[1]
+    else:
+        raise ValueError("layout must be AOS or SOA")
+    n = rows if n is None else int(n)
+    if not 0 <= n <= rows:  # every operand and every out= tensor of a call passes through here with the call's n
+        raise ValueError(f"batch tensor of shape {tuple(t.shape)} holds {rows} instances, the call asks for {n}")
+    return C.c_void_p(t.data_ptr()), n, ld
 
 
 def _out(like, width, layout, n, ld, out=None):
@@ -63,6 +68,20 @@ def _unary(fn, x, win, wout, layout, n, out):
     with torch.cuda.device(x.device):
         check(fn(px, py, n, layout, ld, _stream()))
     return y
+
+
+# ------------------------------------------------------------------------------ MatrixS::operator*
+def matmul(m, n, l, A, B, layout=AOS, count=None, out=None):
+    """MatrixS<m,n>::operator*(MatrixS<n,l>), include/matrixs.hpp:596-640: (., m*n), (., n*l) -> (., m*l);
+    k-j-i accumulation without FMA contraction (bit-identical to the reference's strict build)"""
+    pa, count, ld = _in(A, m * n, layout, count)
+    pb, _, ldb = _in(B, n * l, layout, count)
+    if ldb != ld:
+        raise ValueError("all SOA arrays of one call must share ld")
+    Cm, pc = _out(A, m * l, layout, count, ld, out)
+    with torch.cuda.device(A.device):
+        check(lib.ppx_cuda_batch_matmul(m, n, l, pa, pb, pc, count, layout, ld, _stream()))
+    return Cm
 
 
 # ------------------------------------------------------------------------------ Lie group / algebra
@@ -109,9 +128,9 @@ def se3_adt(xi, layout=AOS, n=None, out=None):
 def SE3_mul(A, B, layout=AOS, n=None, out=None):
     """SE3::operator*, include/liegroup.hpp:204-207"""
     pa, n, ld = _in(A, 16, layout, n)
-    pb, nb, ldb = _in(B, 16, layout, n)
-    if (nb, ldb) != (n, ld):
-        raise ValueError("A and B must have the same batch shape")
+    pb, _, ldb = _in(B, 16, layout, n)
+    if ldb != ld:
+        raise ValueError("all SOA arrays of one call must share ld")
     y, py = _out(A, 16, layout, n, ld, out)
     with torch.cuda.device(A.device):
         check(lib.ppx_cuda_batch_SE3_mul(pa, pb, py, n, layout, ld, _stream()))
@@ -166,9 +185,9 @@ class Kinematics:
         """one step of test/lie_test.cpp:104-110: q + linsolve<SVD>(Js(q), Ad(T) log(T^-1 Ttarget)).x"""
         nj = self.njoints
         pq, n, ld = _in(q, nj, layout, n)
-        pt, nt, ldt = _in(Ttarget, 16, layout, n)
-        if (nt, ldt) != (n, ld):
-            raise ValueError("q and Ttarget must have the same batch shape")
+        pt, _, ldt = _in(Ttarget, 16, layout, n)
+        if ldt != ld:
+            raise ValueError("all SOA arrays of one call must share ld")
         qo, pqo = _out(q, nj, layout, n, ld, out)
         Vs = pV = None
         if want_Vs:
@@ -185,9 +204,9 @@ class Kinematics:
         lo = np.ascontiguousarray(np.full(nj, -big) if lo is None else lo, dtype=np.float64).reshape(nj)
         hi = np.ascontiguousarray(np.full(nj, big) if hi is None else hi, dtype=np.float64).reshape(nj)
         pq, n, ld = _in(init, nj, layout, n)
-        pt, nt, ldt = _in(Ttarget, 16, layout, n)
-        if (nt, ldt) != (n, ld):
-            raise ValueError("init and Ttarget must have the same batch shape")
+        pt, _, ldt = _in(Ttarget, 16, layout, n)
+        if ldt != ld:
+            raise ValueError("all SOA arrays of one call must share ld")
         qo, pqo = _out(init, nj, layout, n, ld)
         status = torch.empty(n, dtype=torch.int8, device=init.device)
         fnorm = torch.empty(n, dtype=torch.float64, device=init.device)
@@ -202,9 +221,9 @@ class Kinematics:
         """the Newton-SVD loop of test/lie_test.cpp:96-113 -> (q, iterations int32[n], status int8[n])"""
         nj = self.njoints
         pq, n, ld = _in(init, nj, layout, n)
-        pt, nt, ldt = _in(Ttarget, 16, layout, n)
-        if (nt, ldt) != (n, ld):
-            raise ValueError("init and Ttarget must have the same batch shape")
+        pt, _, ldt = _in(Ttarget, 16, layout, n)
+        if ldt != ld:
+            raise ValueError("all SOA arrays of one call must share ld")
         qo, pqo = _out(init, nj, layout, n, ld)
         iters = torch.empty(n, dtype=torch.int32, device=init.device)
         status = torch.empty(n, dtype=torch.int8, device=init.device)
@@ -219,9 +238,9 @@ class Kinematics:
 def linsolve(factorization, m, n, A, b, layout=AOS, count=None):
     """linsolve<Factorization::QR|SVD>(A, b), include/linalg.hpp:1189-1209 -> (x, status int8[count])"""
     pa, count, ld = _in(A, m * n, layout, count)
-    pb, cb, ldb = _in(b, m, layout, count)
-    if (cb, ldb) != (count, ld):
-        raise ValueError("A and b must have the same batch shape")
+    pb, _, ldb = _in(b, m, layout, count)
+    if ldb != ld:
+        raise ValueError("all SOA arrays of one call must share ld")
     x, px = _out(A, n, layout, count, ld)
     with torch.cuda.device(A.device):
         if factorization == LU:

@@ -1,16 +1,28 @@
 // host.cu -- the host-buffer face of the C ABI (ppx_cuda_host_*): what a ppx user holding
 // std::vector<ppx::MatrixS<M,N>> calls.  Inputs and outputs are HOST arrays of dense reference
-// records (AoS); the batch is cut into chunks that rotate over a few streams so that the H2D copy of
-// chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap (PCIe is full duplex and,
-// at ~55 GB/s against 6.5 TB/s of HBM, the only thing that matters end to end).  Device scratch comes
-// from the stream-ordered allocator and is released before the call returns.  Pinned host memory
-// (ppx_cuda_malloc_host) makes the copies truly asynchronous; pageable memory works but serialises.
+// records (AoS).  The batch is cut into chunks; on each device a few streams rotate over them so that
+// the H2D copy of one chunk, the kernel of the previous and the D2H copy of the one before overlap
+// (PCIe is full duplex and, at ~55 GB/s against 6.5 TB/s of HBM, the only thing that matters end to end).
+//
+// Several devices (ppx_cuda_host_set_devices / PPX_CUDA_DEVICES): one worker thread per device, and the
+// chunks are handed out from ONE shared queue, a chunk at a time, to whichever device has a free slot.
+// Instances are independent, so which device computes a chunk cannot change a bit of the result
+// (G-device output == 1-device output, bitwise); the queue instead of fixed ceil(n/G) blocks
+// is there because the PCIe rate the devices of one host get under load is uneven (shared root ports,
+// host memory on one socket): with fixed blocks the call ends when the slowest device does, with the
+// queue every link stays busy until the batch is empty.
+//
 // Streams and device scratch are kept between calls (per device: a few non-blocking streams and a memory pool that
 // retains up to PPX_HOST_POOL_MIB, default 1024, of freed scratch), so a small call costs tens of microseconds instead
 // of the ~0.7 ms that creating a stream and mapping fresh device memory took; ppx_cuda_host_trim() gives it back.
+// After a failed call the streams it used are destroyed, not recycled: a later call starts from clean ones.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "ppx_launch.cuh"
@@ -30,8 +42,9 @@ struct HostOut
 };
 
 constexpr int MAX_SLOTS = 8;
-// defaults: 3 chunks in flight, 48 MiB of traffic on the widest side per chunk; PPX_HOST_SLOTS / PPX_HOST_CHUNK_MIB
-// override them (tuning knobs, read once)
+constexpr int MAX_DEVICES = 64;
+// defaults: 3 chunks in flight per device, 48 MiB of traffic on the widest side per chunk; PPX_HOST_SLOTS /
+// PPX_HOST_CHUNK_MIB override them (tuning knobs, read once)
 inline int env_slots()
 {
     static const int v = [] {
@@ -51,13 +64,65 @@ inline size_t env_chunk_bytes()
     return v;
 }
 
+// ---- the devices the host face spreads a batch over ------------------------------------------------------------
+std::mutex g_dev_mu;
+std::vector<int> g_devices;  // empty: the calling thread's current device only
+bool g_devices_set = false;  // false: PPX_CUDA_DEVICES has not been looked at yet
+
+int parse_device_env(std::vector<int> &out)
+{
+    const char *e = std::getenv("PPX_CUDA_DEVICES");
+    out.clear();
+    if (!e || !*e)
+        return PPX_OK;
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess)
+        return PPX_ERR_NO_DEVICE;
+    if (std::strcmp(e, "all") == 0)
+    {
+        for (int d = 0; d < have && d < MAX_DEVICES; d++)
+            out.push_back(d);
+        return PPX_OK;
+    }
+    const char *p = e;
+    while (*p)
+    {
+        char *endp = nullptr;
+        const long d = std::strtol(p, &endp, 10);
+        if (endp == p || d < 0 || d >= have || std::find(out.begin(), out.end(), (int)d) != out.end())
+        {
+            out.clear();
+            return PPX_ERR_BAD_ARGUMENT;
+        }
+        out.push_back((int)d);
+        p = (*endp == ',') ? endp + 1 : endp;
+        if (*endp != ',' && *endp != 0)
+        {
+            out.clear();
+            return PPX_ERR_BAD_ARGUMENT;
+        }
+    }
+    return PPX_OK;
+}
+
+std::vector<int> host_devices()
+{
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    if (!g_devices_set)
+    {
+        parse_device_env(g_devices); // a malformed variable leaves the list empty (current device)
+        g_devices_set = true;
+    }
+    return g_devices;
+}
+
 // per-device resources kept between calls
 struct DevCtx
 {
     std::vector<cudaStream_t> idle; // streams not in use by a call
 };
 std::mutex g_host_mu;
-DevCtx g_host_ctx[64];
+DevCtx g_host_ctx[MAX_DEVICES];
 
 // -> `want` streams and the scratch pool of the current device
 int host_acquire(int want, cudaStream_t *st, cudaMemPool_t &pool, int &device)
@@ -65,7 +130,7 @@ int host_acquire(int want, cudaStream_t *st, cudaMemPool_t &pool, int &device)
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess)
         return (int)e;
-    if (device < 0 || device >= 64)
+    if (device < 0 || device >= MAX_DEVICES)
         return PPX_ERR_NO_DEVICE;
     const int prc = ppx_scratch_pool(device, &pool);
     if (prc != PPX_OK)
@@ -92,8 +157,18 @@ int host_acquire(int want, cudaStream_t *st, cudaMemPool_t &pool, int &device)
     }
     return PPX_OK;
 }
-void host_release(int device, int n, cudaStream_t *st)
+// healthy streams go back to the idle list; after a failure they are destroyed so that nothing a faulted call
+// touched is handed to the next one
+void host_release(int device, int n, cudaStream_t *st, bool healthy)
 {
+    if (!healthy)
+    {
+        for (int s = 0; s < n; s++)
+            if (st[s])
+                cudaStreamDestroy(st[s]);
+        (void)cudaGetLastError();
+        return;
+    }
     std::lock_guard<std::mutex> lock(g_host_mu);
     for (int s = 0; s < n; s++)
         if (st[s])
@@ -111,7 +186,107 @@ void host_release(int device, int n, cudaStream_t *st)
         }                             \
     } while (0)
 
-// run(count, d_in[], d_out[], stream) launches the AoS kernel for one chunk
+// what one call shares between its device workers
+struct Job
+{
+    const std::vector<HostIn> &ins;
+    const std::vector<HostOut> &outs;
+    size_t n, chunk, nchunks;
+    std::atomic<size_t> next{0}; // next chunk nobody has taken yet
+    std::atomic<int> rc{PPX_OK}; // first failure of any worker
+    Job(const std::vector<HostIn> &i, const std::vector<HostOut> &o, size_t n_, size_t chunk_)
+        : ins(i), outs(o), n(n_), chunk(chunk_), nchunks((n_ + chunk_ - 1) / chunk_)
+    {
+    }
+    void fail(int code)
+    {
+        int ok = PPX_OK;
+        rc.compare_exchange_strong(ok, code);
+    }
+};
+
+// One device's share of a call, on the calling thread's current device: takes chunks from the job's queue until it is
+// empty.  run(count, d_in[], d_out[], stream) launches the AoS kernel for one chunk.  With `shared` (several
+// devices) a slot is only refilled once its previous chunk has completely finished, so that a device never holds
+// more than its `nslots` chunks and the rest of the queue stays available to the others; a single device needs no
+// such wait (stream order does it) and keeps the queue of the copy engines full.
+template <class Run>
+void device_worker(Job &job, Run &run, bool shared)
+{
+    const std::vector<HostIn> &ins = job.ins;
+    const std::vector<HostOut> &outs = job.outs;
+    int rc = PPX_OK;
+    cudaStream_t st[MAX_SLOTS] = {};
+    const int nslots = (int)std::min<size_t>(env_slots(), job.nchunks);
+    std::vector<void *> d_in(nslots * ins.size(), nullptr), d_out(nslots * outs.size(), nullptr);
+    cudaMemPool_t pool = nullptr;
+    int device = 0;
+    rc = host_acquire(nslots, st, pool, device);
+    if (rc != PPX_OK)
+    {
+        job.fail(rc);
+        return;
+    }
+    for (size_t k = 0;; k++)
+    {
+        const int s = (int)(k % nslots);
+        if (k < (size_t)nslots)
+        {
+            for (size_t a = 0; a < ins.size(); a++)
+                PPX_TRY(cudaMallocFromPoolAsync(&d_in[s * ins.size() + a], job.chunk * ins[a].bytes, pool, st[s]));
+            for (size_t a = 0; a < outs.size(); a++)
+                if (outs[a].ptr)
+                    PPX_TRY(cudaMallocFromPoolAsync(&d_out[s * outs.size() + a], job.chunk * outs[a].bytes, pool, st[s]));
+        }
+        else if (shared)
+            PPX_TRY(cudaStreamSynchronize(st[s]));
+        if (job.rc.load(std::memory_order_relaxed) != PPX_OK)
+            break; // another device failed: stop feeding
+        const size_t c = job.next.fetch_add(1, std::memory_order_relaxed);
+        if (c >= job.nchunks)
+            break;
+        const size_t first = c * job.chunk;
+        const size_t cnt = std::min(job.chunk, job.n - first);
+        for (size_t a = 0; a < ins.size(); a++)
+            PPX_TRY(cudaMemcpyAsync(d_in[s * ins.size() + a], (const char *)ins[a].ptr + first * ins[a].bytes,
+                                    cnt * ins[a].bytes, cudaMemcpyHostToDevice, st[s]));
+        rc = run(cnt, &d_in[s * ins.size()], &d_out[s * outs.size()], (void *)st[s]);
+        if (rc != PPX_OK)
+            goto done;
+        for (size_t a = 0; a < outs.size(); a++)
+            if (outs[a].ptr)
+                PPX_TRY(cudaMemcpyAsync((char *)outs[a].ptr + first * outs[a].bytes, d_out[s * outs.size() + a],
+                                        cnt * outs[a].bytes, cudaMemcpyDeviceToHost, st[s]));
+    }
+done:
+    for (int s = 0; s < nslots; s++)
+    {
+        for (size_t a = 0; a < ins.size(); a++)
+            if (d_in[s * ins.size() + a])
+            {
+                const cudaError_t e = cudaFreeAsync(d_in[s * ins.size() + a], st[s]);
+                if (rc == PPX_OK && e != cudaSuccess)
+                    rc = (int)e;
+            }
+        for (size_t a = 0; a < outs.size(); a++)
+            if (d_out[s * outs.size() + a])
+            {
+                const cudaError_t e = cudaFreeAsync(d_out[s * outs.size() + a], st[s]);
+                if (rc == PPX_OK && e != cudaSuccess)
+                    rc = (int)e;
+            }
+        const cudaError_t e = cudaStreamSynchronize(st[s]);
+        if (rc == PPX_OK && e != cudaSuccess)
+            rc = (int)e;
+    }
+    if (rc != PPX_OK)
+    {
+        (void)cudaGetLastError();
+        job.fail(rc);
+    }
+    host_release(device, nslots, st, rc == PPX_OK);
+}
+
 template <class Run>
 int pipeline(const std::vector<HostIn> &ins, const std::vector<HostOut> &outs, size_t n, Run run)
 {
@@ -130,54 +305,37 @@ int pipeline(const std::vector<HostIn> &ins, const std::vector<HostOut> &outs, s
     chunk = (chunk + 1023) / 1024 * 1024;
     chunk = std::min(chunk, n);
 
-    int rc = PPX_OK;
-    const int SLOTS = env_slots();
-    cudaStream_t st[MAX_SLOTS] = {};
-    std::vector<void *> d_in(SLOTS * ins.size(), nullptr), d_out(SLOTS * outs.size(), nullptr);
-    const int nslots = (int)std::min<size_t>(SLOTS, (n + chunk - 1) / chunk);
-    cudaMemPool_t pool = nullptr;
-    int device = 0;
-    rc = host_acquire(nslots, st, pool, device);
-    if (rc != PPX_OK)
-        return rc;
-    for (int s = 0; s < nslots; s++)
+    Job job(ins, outs, n, chunk);
+    const std::vector<int> devs = host_devices();
+    if (devs.empty())
     {
-        for (size_t a = 0; a < ins.size(); a++)
-            PPX_TRY(cudaMallocFromPoolAsync(&d_in[s * ins.size() + a], chunk * ins[a].bytes, pool, st[s]));
-        for (size_t a = 0; a < outs.size(); a++)
-            if (outs[a].ptr)
-                PPX_TRY(cudaMallocFromPoolAsync(&d_out[s * outs.size() + a], chunk * outs[a].bytes, pool, st[s]));
+        device_worker(job, run, false); // the calling thread's current device
+        return job.rc.load();
     }
-    for (size_t first = 0, k = 0; first < n; first += chunk, k++)
-    {
-        const int s = (int)(k % nslots);
-        const size_t cnt = std::min(chunk, n - first);
-        for (size_t a = 0; a < ins.size(); a++)
-            PPX_TRY(cudaMemcpyAsync(d_in[s * ins.size() + a], (const char *)ins[a].ptr + first * ins[a].bytes,
-                                    cnt * ins[a].bytes, cudaMemcpyHostToDevice, st[s]));
-        rc = run(cnt, &d_in[s * ins.size()], &d_out[s * outs.size()], (void *)st[s]);
-        if (rc != PPX_OK)
-            goto done;
-        for (size_t a = 0; a < outs.size(); a++)
-            if (outs[a].ptr)
-                PPX_TRY(cudaMemcpyAsync((char *)outs[a].ptr + first * outs[a].bytes, d_out[s * outs.size() + a],
-                                        cnt * outs[a].bytes, cudaMemcpyDeviceToHost, st[s]));
-    }
-done:
-    for (int s = 0; s < nslots; s++)
-    {
-        for (size_t a = 0; a < ins.size(); a++)
-            if (d_in[s * ins.size() + a])
-                cudaFreeAsync(d_in[s * ins.size() + a], st[s]);
-        for (size_t a = 0; a < outs.size(); a++)
-            if (d_out[s * outs.size() + a])
-                cudaFreeAsync(d_out[s * outs.size() + a], st[s]);
-        cudaError_t e = cudaStreamSynchronize(st[s]);
-        if (rc == PPX_OK && e != cudaSuccess)
-            rc = (int)e;
-    }
-    host_release(device, nslots, st);
-    return rc;
+    int home = -1;
+    cudaError_t e = cudaGetDevice(&home);
+    if (e != cudaSuccess)
+        return (int)e;
+    // one worker per configured device, never more workers than chunks; the calling thread is the first of them
+    const size_t workers = std::min<size_t>(devs.size(), job.nchunks);
+    std::vector<std::thread> th;
+    for (size_t w = 1; w < workers; w++)
+        th.emplace_back([&job, &run, &devs, w] {
+            const cudaError_t se = cudaSetDevice(devs[w]);
+            if (se != cudaSuccess)
+                job.fail((int)se);
+            else
+                device_worker(job, run, true);
+        });
+    e = cudaSetDevice(devs[0]);
+    if (e != cudaSuccess)
+        job.fail((int)e);
+    else
+        device_worker(job, run, workers > 1);
+    for (std::thread &t : th)
+        t.join();
+    cudaSetDevice(home);
+    return job.rc.load();
 }
 
 constexpr size_t D = sizeof(double);
@@ -190,6 +348,144 @@ extern "C"
 {
 
 int ppx_cuda_host_trim(void) { return ppx_scratch_trim(); }
+
+int ppx_cuda_host_set_devices(const int *devices, int count)
+{
+    std::vector<int> v;
+    if (count < 0) // all visible devices
+    {
+        int have = 0;
+        if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1)
+            return PPX_ERR_NO_DEVICE;
+        for (int d = 0; d < have && d < MAX_DEVICES; d++)
+            v.push_back(d);
+    }
+    else if (count > 0)
+    {
+        if (!devices || count > MAX_DEVICES)
+            return PPX_ERR_BAD_ARGUMENT;
+        int have = 0;
+        if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1)
+            return PPX_ERR_NO_DEVICE;
+        for (int i = 0; i < count; i++)
+        {
+            if (devices[i] < 0 || devices[i] >= have || std::find(v.begin(), v.end(), devices[i]) != v.end())
+                return PPX_ERR_BAD_ARGUMENT;
+            v.push_back(devices[i]);
+        }
+    }
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    g_devices.swap(v);
+    g_devices_set = true;
+    return PPX_OK;
+}
+
+int ppx_cuda_host_get_devices(int *devices, int capacity)
+{
+    const std::vector<int> v = host_devices();
+    for (int i = 0; i < (int)v.size() && i < capacity && devices; i++)
+        devices[i] = v[i];
+    return (int)v.size();
+}
+
+// Measurement helper: what the host-device links of the configured devices carry when all of them copy at once.
+// `host` is cut into one contiguous slice per device; every worker copies through its slice in chunks of the
+// pipeline's size (device scratch of two chunks, two streams) again and again until `seconds` have passed, all
+// workers starting together.  direction: 0 H2D, 1 D2H, 2 both at once (one stream each, on the two halves of the
+// slice).  gbs[i] = bytes device i moved / elapsed.  No kernel runs: this is the ceiling of any host-buffer path.
+int ppx_cuda_host_copy_probe(void *host, size_t bytes, int direction, double seconds, double *gbs)
+{
+    if (!host || !gbs || bytes == 0 || direction < 0 || direction > 2 || !(seconds > 0.0))
+        return PPX_ERR_BAD_ARGUMENT;
+    std::vector<int> devs = host_devices();
+    int home = -1;
+    cudaError_t e = cudaGetDevice(&home);
+    if (e != cudaSuccess)
+        return (int)e;
+    if (devs.empty())
+        devs.push_back(home);
+    const size_t G = devs.size();
+    const size_t slice = bytes / G / 4096 * 4096;
+    const size_t piece = std::min(env_chunk_bytes(), slice / 2 / 4096 * 4096);
+    if (piece == 0)
+        return PPX_ERR_BAD_ARGUMENT;
+    std::atomic<int> ready{0}, rc{PPX_OK};
+    auto work = [&](size_t w) {
+        cudaStream_t st[2] = {};
+        char *d[2] = {};
+        int err = PPX_OK;
+        auto fail = [&](cudaError_t ce) {
+            if (ce != cudaSuccess && err == PPX_OK)
+                err = (int)ce;
+        };
+        fail(cudaSetDevice(devs[w]));
+        for (int k = 0; k < 2 && err == PPX_OK; k++)
+        {
+            fail(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
+            fail(cudaMalloc((void **)&d[k], piece));
+        }
+        ready.fetch_add(1);
+        while (ready.load() < (int)G) // aligned start
+            std::this_thread::yield();
+        char *h = (char *)host + w * slice;
+        const size_t half = slice / 2;
+        size_t moved = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        double dt = 0.0;
+        size_t off = 0;
+        while (err == PPX_OK)
+        {
+            for (int k = 0; k < 2 && err == PPX_OK; k++)
+            {
+                // stream k walks half k of the slice; direction 2: stream 0 reads the host (H2D), stream 1 writes it
+                const bool to_host = direction == 1 || (direction == 2 && k == 1);
+                char *hp = h + k * half + off;
+                fail(to_host ? cudaMemcpyAsync(hp, d[k], piece, cudaMemcpyDeviceToHost, st[k])
+                             : cudaMemcpyAsync(d[k], hp, piece, cudaMemcpyHostToDevice, st[k]));
+            }
+            for (int k = 0; k < 2; k++)
+                fail(cudaStreamSynchronize(st[k]));
+            moved += 2 * piece;
+            off += piece;
+            if (off + piece > half)
+                off = 0;
+            dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (dt >= seconds)
+                break;
+        }
+        gbs[w] = dt > 0.0 ? (double)moved / dt * 1e-9 : 0.0;
+        for (int k = 0; k < 2; k++)
+        {
+            if (d[k])
+                cudaFree(d[k]);
+            if (st[k])
+                cudaStreamDestroy(st[k]);
+        }
+        if (err != PPX_OK)
+        {
+            int ok = PPX_OK;
+            rc.compare_exchange_strong(ok, err);
+        }
+    };
+    std::vector<std::thread> th;
+    for (size_t w = 1; w < G; w++)
+        th.emplace_back(work, w);
+    work(0);
+    for (std::thread &t : th)
+        t.join();
+    cudaSetDevice(home);
+    return rc.load();
+}
+
+int ppx_cuda_host_matmul(int m, int n, int l, const double *A, const double *B, double *C, size_t count)
+{
+    if (m < 1 || n < 1 || l < 1 || m > 8 || n > 8 || l > 8)
+        return PPX_ERR_BAD_SHAPE;
+    return pipeline({{A, (size_t)m * n * D}, {B, (size_t)n * l * D}}, {{C, (size_t)m * l * D}}, count,
+                    [=](size_t c, void **i, void **o, void *s) {
+                        return ppx_cuda_batch_matmul(m, n, l, (cd)i[0], (cd)i[1], (md)o[0], c, PPX_LAYOUT_AOS, 0, s);
+                    });
+}
 
 int ppx_cuda_host_so3_exp(const double *w, double *R, size_t n)
 {

@@ -435,14 +435,17 @@ int launch_persistent(int block, size_t smem, const Args &a, size_t n, size_t ld
     cudaError_t e = cudaMallocFromPoolAsync((void **)&next, sizeof(*next), pool, s);
     if (e != cudaSuccess)
         return (int)e;
-    cudaMemsetAsync(next, 0, sizeof(*next), s);
-    const size_t want = (n + block - 1) / block;
-    const size_t cap = (size_t)info.sms * per_sm;
-    Kern<<<(unsigned)(want < cap ? want : cap), block, smem, s>>>(a, n, ld, next);
-    g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);
-    e = cudaPeekAtLastError();
-    cudaFreeAsync(next, s);
-    return (int)e;
+    e = cudaMemsetAsync(next, 0, sizeof(*next), s);
+    if (e == cudaSuccess)
+    {
+        const size_t want = (n + block - 1) / block;
+        const size_t cap = (size_t)info.sms * per_sm;
+        Kern<<<(unsigned)(want < cap ? want : cap), block, smem, s>>>(a, n, ld, next);
+        g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);
+        e = cudaPeekAtLastError();
+    }
+    const cudaError_t fe = cudaFreeAsync(next, s);
+    return (int)(e != cudaSuccess ? e : fe);
 }
 
 } // namespace

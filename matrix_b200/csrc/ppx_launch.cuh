@@ -140,21 +140,21 @@ struct DeviceInfo
 
 inline int device_info(DeviceInfo &info, int &device)
 {
-    static DeviceInfo cache[64];
+    static std::atomic<int> cache[64]; // SM count per device, 0 = not asked yet (host threads may race here)
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess)
         return (int)e;
     if (device < 0 || device >= 64)
         return PPX_ERR_NO_DEVICE;
-    if (cache[device].sms == 0)
+    int sms = cache[device].load(std::memory_order_relaxed);
+    if (sms == 0)
     {
-        int sms = 0;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         if (e != cudaSuccess)
             return (int)e;
-        cache[device].sms = sms;
+        cache[device].store(sms, std::memory_order_relaxed);
     }
-    info = cache[device];
+    info.sms = sms;
     return PPX_OK;
 }
 
@@ -176,8 +176,10 @@ int launch(const Op &op, size_t n, size_t ld, void *stream)
         return rc;
     auto kern = pick_kernel<LAYOUT, Op>();
     const size_t smem = TileIO<LAYOUT>::smem_bytes(Op::BLOCK, Op::MAXW) + stage_bytes<LAYOUT, Op>();
-    static int blocks_per_sm[64]; // per instantiation, per device
-    if (blocks_per_sm[device] == 0)
+    static std::atomic<int> blocks_per_sm[64]; // per instantiation, per device; 0 = not asked yet.  Two host threads
+                                               // may both ask (same answer, idempotent attribute), never tear
+    int per_sm = blocks_per_sm[device].load(std::memory_order_relaxed);
+    if (per_sm == 0)
     {
         if (smem > 48 * 1024)
         {
@@ -189,10 +191,11 @@ int launch(const Op &op, size_t n, size_t ld, void *stream)
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, Op::BLOCK, smem);
         if (e != cudaSuccess)
             return (int)e;
-        blocks_per_sm[device] = b > 0 ? b : 1;
+        per_sm = b > 0 ? b : 1;
+        blocks_per_sm[device].store(per_sm, std::memory_order_relaxed);
     }
     const size_t tiles = (n + Op::BLOCK - 1) / Op::BLOCK;
-    const size_t cap = (size_t)info.sms * blocks_per_sm[device] * GRID_WAVES;
+    const size_t cap = (size_t)info.sms * per_sm * GRID_WAVES;
     const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
     kern<<<grid, Op::BLOCK, smem, (cudaStream_t)stream>>>(op, n, ld);
     g_ppx_launch_count.fetch_add(1, std::memory_order_relaxed);

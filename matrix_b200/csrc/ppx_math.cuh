@@ -577,12 +577,12 @@ PPX_DEV int linsolve_qr(double (&A)[M * N], double (&b)[M], double (&x)[N])
 // The permutation is applied to the right-hand sides as it happens, which is what LU::solve's b[indx[row]] does.
 // NRHS right-hand sides are carried along in B (column-major N x NRHS).  Returns the reference's `even` flag in
 // `even`; on SINGULAR the factorisation stops being meaningful and the caller substitutes the reference's result.
+// ipiv[k] receives 1 / u_kk.
 template <int N, int NRHS>
-PPX_DEV bool lu_factor_solve(double (&A)[N * N], double (&B)[N * (NRHS > 0 ? NRHS : 1)], bool &even)
+PPX_DEV bool lu_factor_solve(double (&A)[N * N], double (&B)[N * (NRHS > 0 ? NRHS : 1)], bool &even, double (&ipiv)[N])
 {
     bool singular = false;
     even = true;
-    double ipiv[N];
 #pragma unroll
     for (int k = 0; k < N; k++)
     {
@@ -649,6 +649,44 @@ PPX_DEV bool lu_factor_solve(double (&A)[N * N], double (&B)[N * (NRHS > 0 ? NRH
     }
     return singular;
 }
+template <int N, int NRHS>
+PPX_DEV bool lu_factor_solve(double (&A)[N * N], double (&B)[N * (NRHS > 0 ? NRHS : 1)], bool &even)
+{
+    double ipiv[N];
+    return lu_factor_solve<N, NRHS>(A, B, even, ipiv);
+}
+
+// Rigorous upper bound of cond_inf(A) from the partial-pivoting factors P A = L U held in `lu` (multipliers below the
+// diagonal, |l_ij| <= 1; U on and above it; ipiv[k] = 1/u_kk):
+//   |A|_inf <= |L|_inf |U|_inf <= N |U|_inf,     |A^-1|_inf <= |U^-1|_inf |L^-1|_inf <= |M(U)^-1 e|_inf 2^(N-1),
+// where M(U) is U's comparison matrix (|u_ii| on the diagonal, -|u_ij| above it): M(U)^-1 >= |U^-1| entrywise, so one
+// back substitution with absolute values bounds the norm of the inverse (Higham, "A survey of condition number
+// estimation for triangular matrices", SIAM Rev. 29, 1987).  On 6x6 matrices the bound exceeds the true condition
+// number by 10-300x (uniform random entries, UR5 Jacobians); zero, inf and NaN pivots give inf or NaN.
+template <int N>
+PPX_DEV double lu_cond_bound(const double (&lu)[N * N], const double (&ipiv)[N])
+{
+    double z[N], zmax = 0.0, unorm = 0.0;
+#pragma unroll
+    for (int i = N - 1; i >= 0; i--)
+    {
+        double acc = 1.0, row = fabs(lu[i + i * N]);
+#pragma unroll
+        for (int j = i + 1; j < N; j++)
+        {
+            acc = fma(fabs(lu[i + j * N]), z[j], acc);
+            row += fabs(lu[i + j * N]);
+        }
+        z[i] = acc * fabs(ipiv[i]);
+        zmax = z[i] > zmax ? z[i] : zmax; // a NaN z[i] leaves zmax alone but poisons every later z: caught via z[0]
+        unorm = row > unorm ? row : unorm;
+    }
+    const double b = ((double)N * (double)(1 << (N - 1))) * unorm * zmax;
+    return z[0] == z[0] ? b : z[0]; // NaN in, NaN out
+}
+// the LU shortcut of the square pseudo-inverse solve is taken below this bound: SVD::solve's truncation
+// (0.5 sqrt(2n+1) eps w_max, linalg.hpp:889-901) acts only beyond cond_2 ~ 2.5e15 >> N * 1e10
+constexpr double SQUARE_LU_COND_MAX = 1e10;
 
 // MatrixS::I() (include/linalg.hpp:933-948: LU with partial pivoting, then one solve per unit vector; {} when SINGULAR)
 // as an in-place Gauss-Jordan elimination with the same pivoting: the candidates for pivot k are the entries the LU
@@ -1096,10 +1134,12 @@ PPX_DEV void jacobi_rowsolve(const double (&A)[N * N], const double (&b)[N], dou
 // linsolve<Factorization::SVD> on a SQUARE system (SVD::solve, linalg.hpp:886-913) = A^+ b with singular values below
 // 0.5 sqrt(2n+1) w_max EPS_DP dropped.  That truncation can only act when cond(A) > ~2e15; everywhere else A^+ b is
 // A^-1 b, and a backward-stable solver returns it to the same accuracy (~cond eps) whatever the factorisation.  So the
-// system is first solved by LU with partial pivoting (~1/30 of the arithmetic of the Jacobi solve); if any pivot falls
-// below 1e-8 of the largest one -- seven orders of magnitude before truncation could matter, also catching zero, inf and
-// NaN pivots -- the row-orthogonalising Jacobi solve is run as well and its result taken for those lanes.  The decision
-// to run it is per warp, so well-conditioned batches never execute it.  `allow_lu = false` forces the Jacobi path.
+// system is first solved by LU with partial pivoting (~1/30 of the arithmetic of the Jacobi solve) and a rigorous upper
+// bound of cond_inf(A) is read off the factors (lu_cond_bound -- pivot ratios alone do not bound the condition number:
+// I + 1e3 triu(ones) has unit pivots and cond 3.5e18).  Unless that bound is below 1e10 -- five orders of magnitude
+// before truncation could matter; false for zero, inf and NaN pivots -- the row-orthogonalising Jacobi solve is run as
+// well and its result taken for those lanes.  The decision to run it is per warp, so well-conditioned batches never
+// execute it.  `allow_lu = false` forces the Jacobi path.
 template <int N>
 PPX_DEV void square_pinv_solve(const double (&A)[N * N], const double (&b)[N], double (&x)[N], bool allow_lu)
 {
@@ -1115,15 +1155,9 @@ PPX_DEV void square_pinv_solve(const double (&A)[N * N], const double (&b)[N], d
         for (int i = 0; i < N * N; i++)
             lu[i] = A[i];
         bool even;
-        lu_factor_solve<N, 1>(lu, rx, even);
-        double pmax = 0.0;
-#pragma unroll
-        for (int k = 0; k < N; k++)
-            pmax = fmax(pmax, fabs(lu[k + k * N]));
-        easy = true;
-#pragma unroll
-        for (int k = 0; k < N; k++)
-            easy = easy && fabs(lu[k + k * N]) > 1e-8 * pmax;
+        double ipiv[N];
+        lu_factor_solve<N, 1>(lu, rx, even, ipiv);
+        easy = lu_cond_bound<N>(lu, ipiv) < SQUARE_LU_COND_MAX;
         if (__all_sync(0xffffffffu, easy))
         {
 #pragma unroll

@@ -322,8 +322,9 @@ struct OpPinv
     const double *A;
     double *P; // N x M
     bool allow_lu;
-    // A square matrix whose pivots all lie within 1e-8 of the largest is inverted by Gauss-Jordan elimination: the
-    // truncation below cannot act before cond ~ 2e15, so pinv(A) = A^-1 there (the argument of square_pinv_solve)
+    // A square matrix with |A|_inf |A^-1|_inf < 1e10 (measured on the computed inverse) is inverted by Gauss-Jordan
+    // elimination: the truncation below cannot act before cond ~ 2e15, so pinv(A) = A^-1 there (the argument of
+    // square_pinv_solve; pivot ratios alone would not do, they do not bound the condition number)
     template <class IO, int MM = M>
     __device__ __forceinline__ typename std::enable_if<MM == N, bool>::type fast_square(const IO &io, const double (&a)[M * N],
                                                                                       int shift, double (&g)[N * M]) const
@@ -335,7 +336,21 @@ struct OpPinv
             g[i] = a[i];
         double pmin, pmax;
         gauss_jordan_inverse<N>(g, pmin, pmax);
-        const bool easy = pmin > 1e-8 * pmax && pmax < DBL_MAX; // false for zero, inf and NaN pivots
+        double na = 0.0, ng = 0.0; // inf-norms (max absolute row sum) of A and of the computed inverse
+#pragma unroll
+        for (int r = 0; r < N; r++)
+        {
+            double ra = 0.0, rg = 0.0;
+#pragma unroll
+            for (int c = 0; c < N; c++)
+            {
+                ra += fabs(a[r + c * N]);
+                rg += fabs(g[r + c * N]);
+            }
+            na = ra > na ? ra : na;
+            ng = (rg > ng || rg != rg) ? rg : ng; // a NaN row sum sticks
+        }
+        const bool easy = na * ng < SQUARE_LU_COND_MAX && pmin > 0.0 && pmax < DBL_MAX; // false for zero, inf, NaN pivots
         pow2_rescale(g, shift);
         if (__all_sync(0xffffffffu, easy))
             io.store(P, g);

@@ -2,8 +2,14 @@
 // generator and the fp64 peak probe.  None of this is on the timed hot path.
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include <sys/mman.h>
 
 #include "ppx_launch.cuh"
 
@@ -133,6 +139,16 @@ __global__ void k_probe_write(double *__restrict__ out, int planes, size_t n, si
     }
 }
 
+// blocks handed out by ppx_cuda_malloc_host's mapped path: user pointer -> (mapping, its length, registered length)
+struct HostBlock
+{
+    void *raw;
+    size_t raw_len;
+    size_t len;
+};
+std::mutex g_hb_mu;
+std::unordered_map<void *, HostBlock> g_hb;
+
 int grid_for(size_t n, int block)
 {
     int dev = 0, sms = 148;
@@ -172,8 +188,79 @@ int ppx_cuda_device_count(void)
 int ppx_cuda_set_device(int device) { return (int)cudaSetDevice(device); }
 int ppx_cuda_malloc(void **dptr, size_t bytes) { return (int)cudaMalloc(dptr, bytes); }
 int ppx_cuda_free(void *dptr) { return (int)cudaFree(dptr); }
-int ppx_cuda_malloc_host(void **hptr, size_t bytes) { return (int)cudaMallocHost(hptr, bytes); }
-int ppx_cuda_free_host(void *hptr) { return (int)cudaFreeHost(hptr); }
+// Pinned host memory.  Small blocks come from cudaHostAlloc.  Large ones (>= 64 MiB) are mapped here, advised to use
+// transparent huge pages (PPX_HOST_HUGEPAGES=0 turns that off), faulted in by several threads at once -- a single
+// thread zero-filling 4 KiB pages manages ~1-2 GB/s, which is what made an 8 GB cudaHostAlloc take seconds -- and then
+// page-locked with ONE cudaHostRegister(Portable), so that a copy may span any part of the block and every device of
+// the process can DMA to it.
+int ppx_cuda_malloc_host(void **hptr, size_t bytes)
+{
+    if (!hptr)
+        return PPX_ERR_BAD_ARGUMENT;
+    *hptr = nullptr;
+    if (bytes == 0)
+        return PPX_OK;
+    const char *mode = std::getenv("PPX_HOST_ALLOC"); // "cuda": always cudaHostAlloc
+    const bool map_it = bytes >= ((size_t)64 << 20) && !(mode && std::strcmp(mode, "cuda") == 0);
+    if (map_it)
+    {
+        constexpr size_t HUGE = (size_t)2 << 20;
+        const size_t len = (bytes + HUGE - 1) / HUGE * HUGE;
+        void *raw = mmap(nullptr, len + HUGE, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (raw != MAP_FAILED)
+        {
+            char *p = (char *)(((uintptr_t)raw + HUGE - 1) / HUGE * HUGE);
+            const char *hp = std::getenv("PPX_HOST_HUGEPAGES");
+            if (!(hp && std::atoi(hp) == 0))
+                madvise(p, len, MADV_HUGEPAGE);
+            unsigned nt = std::thread::hardware_concurrency();
+            nt = nt == 0 ? 4 : (nt > 16 ? 16 : nt);
+            const size_t slices = std::min<size_t>(nt, len / ((size_t)32 << 20) + 1);
+            std::vector<std::thread> th;
+            for (size_t t = 0; t < slices; t++)
+                th.emplace_back([=] {
+                    const size_t lo = len / slices * t, hi = t + 1 == slices ? len : len / slices * (t + 1);
+                    for (size_t o = lo; o < hi; o += 4096)
+                        ((volatile char *)p)[o] = 0;
+                });
+            for (std::thread &t : th)
+                t.join();
+            const cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable);
+            if (e == cudaSuccess)
+            {
+                std::lock_guard<std::mutex> lock(g_hb_mu);
+                g_hb[p] = HostBlock{raw, len + HUGE, len};
+                *hptr = p;
+                return PPX_OK;
+            }
+            (void)cudaGetLastError(); // registration refused (locked-memory limit, ...): fall back to the runtime's allocator
+            munmap(raw, len + HUGE);
+        }
+    }
+    return (int)cudaHostAlloc(hptr, bytes, cudaHostAllocPortable);
+}
+int ppx_cuda_free_host(void *hptr)
+{
+    if (!hptr)
+        return PPX_OK;
+    HostBlock b{};
+    bool mapped = false;
+    {
+        std::lock_guard<std::mutex> lock(g_hb_mu);
+        auto it = g_hb.find(hptr);
+        if (it != g_hb.end())
+        {
+            b = it->second;
+            mapped = true;
+            g_hb.erase(it);
+        }
+    }
+    if (!mapped)
+        return (int)cudaFreeHost(hptr);
+    const cudaError_t e = cudaHostUnregister(hptr);
+    munmap(b.raw, b.raw_len);
+    return (int)e;
+}
 
 int ppx_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream)
 {

@@ -11,16 +11,63 @@ import numpy as np
 from ._lib import check, lib
 
 
+class _PinnedBlock:
+    """One ppx_cuda_malloc_host block; freed when the last numpy view of it is collected."""
+
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        check(lib.ppx_cuda_malloc_host(C.byref(p), max(int(nbytes), 1)))
+        self.ptr = p.value
+
+    def __del__(self):
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if ptr:
+            try:
+                lib.ppx_cuda_free_host(C.c_void_p(ptr))
+            except Exception:  # interpreter shutdown
+                pass
+
+
 def pinned_empty(shape, dtype=np.float64):
-    """numpy array backed by page-locked host memory (owned by a torch pinned tensor)."""
-    import torch
-    t = torch.empty(tuple(np.atleast_1d(shape)), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
-    a = t.numpy()
-    _KEEP[a.__array_interface__["data"][0]] = t
-    return a
+    """numpy array backed by page-locked host memory from ppx_cuda_malloc_host (DMA-able by every device of the
+    process).  The block is returned to the driver when the array and all its views are gone."""
+    shape = tuple(int(x) for x in np.atleast_1d(shape))
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    block = _PinnedBlock(nbytes)
+    buf = (C.c_char * max(nbytes, 1)).from_address(block.ptr)
+    buf._ppx_block = block  # the ctypes buffer is the numpy array's base: it keeps the block alive
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
 
 
-_KEEP = {}
+def set_devices(devices):
+    """Devices the host-buffer calls spread a batch over: a list of ordinals, "all", or None / [] for the calling
+    thread's current device only (ppx_cuda_host_set_devices)."""
+    if devices is None or (not isinstance(devices, str) and len(devices) == 0):
+        check(lib.ppx_cuda_host_set_devices(None, 0))
+    elif isinstance(devices, str):
+        if devices != "all":
+            raise ValueError('devices must be a list of ordinals, "all" or None')
+        check(lib.ppx_cuda_host_set_devices(None, -1))
+    else:
+        arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+        check(lib.ppx_cuda_host_set_devices(arr, len(devices)))
+
+
+def get_devices():
+    arr = (C.c_int * 64)()
+    n = lib.ppx_cuda_host_get_devices(arr, 64)
+    return [arr[i] for i in range(n)]
+
+
+def copy_probe(host_array, direction, seconds=1.0):
+    """GB/s each configured device sustains while all of them copy through `host_array` (pinned) at once;
+    direction "h2d", "d2h" or "both" (ppx_cuda_host_copy_probe)."""
+    n = max(len(get_devices()), 1)
+    out = (C.c_double * n)()
+    d = {"h2d": 0, "d2h": 1, "both": 2}[direction]
+    check(lib.ppx_cuda_host_copy_probe(C.c_void_p(host_array.ctypes.data), host_array.nbytes, d, float(seconds), out))
+    return [out[i] for i in range(n)]
 
 
 def _p(a):
@@ -33,10 +80,19 @@ def _arr(a, width):
     return a
 
 
+def _same_rows(n, **arrays):
+    for name, a in arrays.items():
+        if a.shape[0] != n:
+            raise ValueError(f"{name} holds {a.shape[0]} records, expected {n}")
+
+
 def _outbuf(out, n, width, dtype=np.float64):
     if out is None:
         return np.empty((n, width) if width else (n,), dtype=dtype)
-    assert out.flags.c_contiguous and out.dtype == dtype and out.size == n * max(width, 1)
+    if not (isinstance(out, np.ndarray) and out.flags.c_contiguous and out.flags.writeable and out.dtype == dtype
+            and out.size == n * max(width, 1)):
+        raise ValueError(f"out must be a writable C-contiguous {np.dtype(dtype).name} array of {n} x {max(width, 1)} "
+                         "elements")
     return out
 
 
@@ -44,6 +100,15 @@ def _unary(fn, x, win, wout, out):
     x = _arr(x, win)
     y = _outbuf(out, x.shape[0], wout)
     check(fn(_p(x), _p(y), x.shape[0]))
+    return y
+
+
+def matmul(m, n, l, A, B, out=None):
+    """MatrixS<m,n>::operator* over host records (include/matrixs.hpp:596-640)"""
+    A, B = _arr(A, m * n), _arr(B, n * l)
+    _same_rows(A.shape[0], B=B)
+    y = _outbuf(out, A.shape[0], m * l)
+    check(lib.ppx_cuda_host_matmul(m, n, l, _p(A), _p(B), _p(y), A.shape[0]))
     return y
 
 
@@ -81,6 +146,7 @@ def se3_adt(xi, out=None):
 
 def SE3_mul(A, B, out=None):
     A, B = _arr(A, 16), _arr(B, 16)
+    _same_rows(A.shape[0], B=B)
     y = _outbuf(out, A.shape[0], 16)
     check(lib.ppx_cuda_host_SE3_mul(_p(A), _p(B), _p(y), A.shape[0]))
     return y
@@ -119,6 +185,7 @@ class Kinematics:
     def ik_newton_step(self, q, Ttarget, want_Vs=False, out=None):
         q, Tt = _arr(q, self.njoints), _arr(Ttarget, 16)
         n = q.shape[0]
+        _same_rows(n, Ttarget=Tt)
         qo = _outbuf(out, n, self.njoints)
         Vs = np.empty((n, 6)) if want_Vs else None
         check(lib.ppx_cuda_host_ik_newton_step(_p(self.screws), _p(self.home), self.njoints, _p(q), _p(Tt), _p(qo),
@@ -133,6 +200,7 @@ class Kinematics:
         hi = np.ascontiguousarray(np.full(nj, big) if hi is None else hi, dtype=np.float64).reshape(nj)
         q, Tt = _arr(init, nj), _arr(Ttarget, 16)
         n = q.shape[0]
+        _same_rows(n, Ttarget=Tt)
         qo = np.empty((n, nj))
         status = np.empty(n, dtype=np.int8)
         fnorm = np.empty(n)
@@ -143,6 +211,7 @@ class Kinematics:
     def inverseSpaceNewton(self, Ttarget, init, max_iter=20):
         q, Tt = _arr(init, self.njoints), _arr(Ttarget, 16)
         n = q.shape[0]
+        _same_rows(n, Ttarget=Tt)
         qo = np.empty((n, self.njoints))
         iters = np.empty(n, dtype=np.int32)
         status = np.empty(n, dtype=np.int8)
@@ -154,6 +223,7 @@ class Kinematics:
 def linsolve(factorization, m, n, A, b):
     A, b = _arr(A, m * n), _arr(b, m)
     cnt = A.shape[0]
+    _same_rows(cnt, b=b)
     x = np.empty((cnt, n))
     if factorization == "LU":
         st = np.empty(cnt, dtype=np.int8)
@@ -165,7 +235,7 @@ def linsolve(factorization, m, n, A, b):
         st = np.zeros(cnt, dtype=np.int8)
         check(lib.ppx_cuda_host_linsolve_svd(m, n, _p(A), _p(b), _p(x), cnt))
     else:
-        raise ValueError("factorization must be 'QR' or 'SVD'")
+        raise ValueError("factorization must be 'LU', 'QR' or 'SVD'")
     return x, st
 
 

@@ -974,6 +974,14 @@ int ppxo_se3_exp(const double *xi, double *T, size_t count, int nthreads) LOOP(s
 int ppxo_SE3_log(const double *T, double *xi, size_t count, int nthreads) LOOP(SE3_log1(T + 16 * i, xi + 6 * i);)
 int ppxo_se3_exp_log(const double *xi, double *xo, size_t count, int nthreads)
     LOOP(double T[16]; se3_exp1(xi + 6 * i, T); SE3_log1(T, xo + 6 * i);)
+/* MatrixS::operator*, include/matrixs.hpp:596-640 */
+int ppxo_matmul(int m, int n, int l, const double *A, const double *B, double *C, size_t count, int nthreads)
+{
+    if (m < 1 || n < 1 || l < 1)
+        return -1;
+    LOOP(gemm(m, n, l, A + (size_t)m * n * i, B + (size_t)n * l * i, C + (size_t)m * l * i);)
+}
+
 int ppxo_SE3_mul(const double *A, const double *B, double *C, size_t count, int nthreads)
     LOOP(gemm(4, 4, 4, A + 16 * i, B + 16 * i, C + 16 * i);)
 int ppxo_SE3_inv(const double *T, double *Ti, size_t count, int nthreads) LOOP(SE3_inv1(T + 16 * i, Ti + 16 * i);)

@@ -37,6 +37,9 @@ extern "C" {
 const char *ppxo_kind(void);    /* "reference" | "port" */
 int ppxo_max_threads(void);
 
+/* MatrixS<m,n>::operator*(MatrixS<n,l>), matrixs.hpp:596-640; the reference shim instantiates
+ * (3,3,3) (4,4,4) (6,6,6) (6,6,1) (4,4,1) (3,3,1) (4,3,3) (5,4,2) (2,7,3), the port takes any shape */
+int ppxo_matmul(int m, int n, int l, const double *A, const double *B, double *C, size_t count, int nthreads);
 /* liegroup.hpp:116-133 / :60-92 */
 int ppxo_so3_exp(const double *w, double *R, size_t count, int nthreads);
 int ppxo_SO3_log(const double *R, double *w, size_t count, int nthreads);

@@ -334,6 +334,25 @@ extern "C"
     {
         PPXO_LOOP(store(xo + 6 * i, load<6, 1>(xi + 6 * i).exp().log());)
     }
+#define PPXO_MATMUL(M_, N_, L_)                                                                                  \
+    if (m == M_ && n == N_ && l == L_)                                                                           \
+    {                                                                                                            \
+        PPXO_LOOP(store(C + M_ * L_ * i, load<M_, N_>(A + M_ * N_ * i) * load<N_, L_>(B + N_ * L_ * i));)        \
+    }
+    int ppxo_matmul(int m, int n, int l, const double *A, const double *B, double *C, size_t count, int nthreads)
+    {
+        // MatrixS<M,N>::operator*(const MatrixS<N,L> &), include/matrixs.hpp:596-640
+        PPXO_MATMUL(3, 3, 3)
+        PPXO_MATMUL(4, 4, 4)
+        PPXO_MATMUL(6, 6, 6)
+        PPXO_MATMUL(6, 6, 1)
+        PPXO_MATMUL(4, 4, 1)
+        PPXO_MATMUL(3, 3, 1)
+        PPXO_MATMUL(4, 3, 3)
+        PPXO_MATMUL(5, 4, 2)
+        PPXO_MATMUL(2, 7, 3)
+        return -1;
+    }
     int ppxo_SE3_mul(const double *A, const double *B, double *C, size_t count, int nthreads)
     {
         PPXO_LOOP(store(C + 16 * i, MatrixS<4, 4>(SE3(load<4, 4>(A + 16 * i)) * SE3(load<4, 4>(B + 16 * i))));) // liegroup.hpp:204-207

@@ -40,6 +40,20 @@ def ref_strict():
     return Oracle("ref_strict")
 
 
+@pytest.fixture(scope="session", params=["port", "ref_strict"])
+def cpu_ref(request):
+    """The checker of the headline parity tests, once as the C restatement and once as the compiled reference itself
+    (oracle/_ref/libppx_ref_strict.so: the unmodified ppx headers behind ref_shim.cpp; it ships prebuilt to the GPU
+    box).  The two are pinned bit-for-bit to each other by tests/test_oracle.py."""
+    from oracle_lib import Oracle, available
+    if request.param == "port":
+        _ensure_oracle_port()
+        return Oracle("port")
+    if not available("ref_strict"):
+        pytest.skip("oracle/_ref/libppx_ref_strict.so not built (needs /root/reference)")
+    return Oracle("ref_strict")
+
+
 @pytest.fixture(scope="session")
 def ref():
     from oracle_lib import Oracle, available

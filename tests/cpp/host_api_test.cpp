@@ -159,6 +159,48 @@ int main()
         std::vector<EqnResult<3>> res(n);
         cuda::batch_linsolve<factorization::QR>(A.data(), b.data(), res.data(), n);
         EXPECT(res[31337].x == linsolve<factorization::SVD>(A[31337], b[31337]).x);
+        // MatrixS::operator* (include/matrixs.hpp:596-640) batched: exact k-j-i accumulation, checked bit for bit
+        // against the same loop written out here (this file is compiled without FMA contraction for that)
+        std::vector<Matrix<3, 3>> B3(n);
+        std::vector<Matrix<4, 3>> AB(n);
+        for (std::size_t i = 0; i < n; i++)
+            for (int k = 0; k < 9; k++)
+                B3[i][k] = std::cos(0.37 * (double)(i + 1) * (k + 1));
+        cuda::batch_mul(A.data(), B3.data(), AB.data(), n); // (4,3,3): the generic kernel
+        bool same = true;
+        for (std::size_t i = 0; i < n; i += 997)
+        {
+            double c[12] = {};
+            for (int k = 0; k < 3; k++)
+                for (int j = 0; j < 3; j++)
+                    for (int r = 0; r < 4; r++)
+                        c[r + j * 4] += A[i][r + k * 4] * B3[i][k + j * 3];
+            for (int e = 0; e < 12; e++)
+                same = same && c[e] == AB[i][e];
+        }
+        EXPECT(same);
+        // the whole box behind the same call: every visible device, then back to the current one
+        cuda::use_all_devices();
+        std::vector<SE3> T2(n);
+        std::vector<Matrix<6, 6>> Js2(n);
+        cuda::batch_fk_jacobian(UR5, q.data(), T2.data(), Js2.data(), n);
+        cuda::use_current_device();
+        bool bitwise = true;
+        for (std::size_t i = 0; i < n; i++)
+            bitwise = bitwise && std::equal(T[i].begin(), T[i].end(), T2[i].begin()) &&
+                      std::equal(Js[i].begin(), Js[i].end(), Js2[i].begin());
+        EXPECT(bitwise);
+    }
+    // constructors of include/liegroup.hpp:41-43, 200
+    {
+        SO3 R(so3{0, 1, 0}, so3{-1, 0, 0}, so3{0, 0, 1});
+        EXPECT(R == SO3::RotZ(PI / 2));
+        double rm[3][3] = {{0, -1, 0}, {1, 0, 0}, {0, 0, 1}};
+        EXPECT(SO3(rm) == R);
+        double tm[4][4] = {{0, -1, 0, 0.5}, {1, 0, 0, -2}, {0, 0, 1, 3}, {9, 9, 9, 9}};
+        SE3 Tm(tm);
+        EXPECT(Tm == SE3(R, T3{0.5, -2.0, 3.0}) && Tm(3, 0) == 0.0 && Tm(3, 3) == 1.0);
+        EXPECT((Tm * Tm.I()) == SE3());
     }
     std::printf(failures ? "host_api_test: %d FAILURES\n" : "host_api_test: all passed\n", failures);
     return failures ? 1 : 0;

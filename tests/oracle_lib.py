@@ -94,6 +94,14 @@ class Oracle:
     def se3_adt(self, xi):
         return self._map("ppxo_se3_adt", xi, 6, 36)
 
+    def matmul(self, m, n, l, A, B):
+        A = _in(A, m * n)
+        B = _in(B, n * l)
+        out = np.empty((A.shape[0], m * l))
+        self._call("ppxo_matmul", C.c_int(m), C.c_int(n), C.c_int(l), _d(A), _d(B), _d(out), C.c_size_t(A.shape[0]),
+                   C.c_int(self.nthreads))
+        return out
+
     def SE3_mul(self, A, B):
         A = _in(A, 16)
         B = _in(B, 16)

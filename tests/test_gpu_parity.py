@@ -76,27 +76,27 @@ RAGGED = 1000 * 33 + 7  # not a multiple of the warp, block or tile size
 
 # --------------------------------------------------------------------------------------- Lie ops
 @pytest.mark.parametrize("layout", LAYOUTS)
-def test_se3_exp(mb, port, layout):
+def test_se3_exp(mb, cpu_ref, layout):
     xi = synth.se3_twists(RAGGED)
     T = run(mb, mb.se3_exp, layout, xi)
-    ref = port.se3_exp(xi)
+    ref = cpu_ref.se3_exp(xi)
     assert rel_err(T, ref).max() < REL
     assert np.all(T[:, [3, 7, 11]] == 0.0) and np.all(T[:, 15] == 1.0)
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
-def test_SE3_log_same_inputs(mb, port, layout):
+def test_SE3_log_same_inputs(mb, cpu_ref, layout):
     xi = synth.se3_twists(RAGGED)
-    T = port.se3_exp(xi)
+    T = cpu_ref.se3_exp(xi)
     got = run(mb, mb.SE3_log, layout, T)
-    assert rel_err(got, port.SE3_log(T)).max() < REL
+    assert rel_err(got, cpu_ref.SE3_log(T)).max() < REL
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
-def test_se3_exp_log_fused_round_trip(mb, port, layout):
+def test_se3_exp_log_fused_round_trip(mb, cpu_ref, layout):
     xi = synth.se3_twists(N)  # theta in [0.05, pi - 0.05]
     got = run(mb, mb.se3_exp_log, layout, xi)
-    ref = port.se3_exp_log(xi)
+    ref = cpu_ref.se3_exp_log(xi)
     assert rel_err(got, ref).max() < REL
     assert rel_err(got, xi).max() < 1e-11  # identity, conditioned by 1/sin^2(theta)
 
@@ -132,6 +132,46 @@ def test_lie_edge_cases_against_recorded_reference(mb, fixtures):
     assert np.allclose(np.abs(got[1:4]), np.pi * np.eye(3), atol=1e-15)
 
 
+MATMUL_MENU = [(3, 3, 3), (4, 4, 4), (6, 6, 6), (6, 6, 1), (4, 4, 1), (3, 3, 1)]  # unrolled kernels
+MATMUL_GENERIC = [(4, 3, 3), (5, 4, 2), (2, 7, 3)]                                 # runtime-shape kernel
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("shape", MATMUL_MENU + MATMUL_GENERIC)
+def test_matmul_is_bit_identical_to_the_reference_operator(mb, cpu_ref, layout, shape):
+    """SURVEY 8(a) row a2, MatrixS::operator* (matrixs.hpp:596-640): k-j-i accumulation with separately rounded
+    products and sums -- integer-style parity: every bit equal to the reference built without FMA contraction."""
+    m, n, l = shape
+    cnt = RAGGED if shape in MATMUL_MENU else 4099
+    A = synth.dense(cnt, m, n, seed=0xA20 + m)
+    B = synth.dense(cnt, n, l, seed=0xA40 + l)
+    got = run(mb, lambda a_, b_, layout: mb.matmul(m, n, l, a_, b_, layout=layout), layout, A, B)
+    assert np.array_equal(got, cpu_ref.matmul(m, n, l, A, B))
+
+
+def test_matmul_host_face_and_errors(mb, port):
+    from matrix_b200 import host
+    from matrix_b200._lib import PpxCudaError
+    A, B = synth.dense(300_001, 6, 6, seed=0xA61), synth.dense(300_001, 6, 6, seed=0xA62)
+    assert np.array_equal(host.matmul(6, 6, 6, A, B), port.matmul(6, 6, 6, A, B))
+    with pytest.raises(PpxCudaError):
+        host.matmul(9, 2, 2, np.zeros((4, 18)), np.zeros((4, 4)))
+    with pytest.raises(ValueError):
+        host.matmul(3, 3, 3, np.zeros((4, 9)), np.zeros((5, 9)))
+    # out-of-range explicit n and short second operands are refused before anything is launched (batch._in)
+    a = torch.zeros((8, 9), dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError):
+        mb.matmul(3, 3, 3, a, a[:4].contiguous())
+    with pytest.raises(ValueError):
+        mb.matmul(3, 3, 3, a, a, count=9)
+    with pytest.raises(ValueError):
+        mb.SE3_mul(torch.zeros((8, 16), dtype=torch.float64, device="cuda"),
+                   torch.zeros((7, 16), dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        mb.se3_exp(torch.zeros((8, 6), dtype=torch.float64, device="cuda"),
+                   out=torch.zeros((4, 16), dtype=torch.float64, device="cuda"))
+
+
 @pytest.mark.parametrize("layout", LAYOUTS)
 def test_so3_exp_log_jac(mb, port, layout):
     w = synth.se3_twists(N)[:, :3].copy()
@@ -165,11 +205,11 @@ def test_SE3_mul_inv_Adt_adt(mb, port, layout):
 
 # --------------------------------------------------------------------------------------- kinematics
 @pytest.mark.parametrize("layout", LAYOUTS)
-def test_ur5_fk_jacobian(mb, port, layout):
+def test_ur5_fk_jacobian(mb, cpu_ref, layout):
     kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
     q = synth.joint_angles(RAGGED)
     T, Js = run(mb, kin.fk_jacobian, layout, q)
-    rT, rJ = port.poe_fk_jacobian(synth.UR5_SCREWS, synth.UR5_HOME, q)
+    rT, rJ = cpu_ref.poe_fk_jacobian(synth.UR5_SCREWS, synth.UR5_HOME, q)
     assert rel_err(T, rT).max() < REL
     assert rel_err(Js, rJ).max() < REL
     assert np.array_equal(Js[:, :6], np.broadcast_to(synth.UR5_SCREWS[0], (RAGGED, 6)))  # demo/robotics.hpp:97
@@ -216,12 +256,12 @@ def _ik_inputs(port, n, first=0):
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
-def test_ik_newton_step(mb, port, layout):
+def test_ik_newton_step(mb, cpu_ref, layout):
     n = 1 << 15
     kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
-    q, Tt, kappa = _ik_inputs(port, n)
+    q, Tt, kappa = _ik_inputs(cpu_ref, n)
     qo, Vs = run(mb, kin.ik_newton_step, layout, q, Tt, want_Vs=True)
-    rq, rV = port.ik_newton_step(synth.UR5_SCREWS, synth.UR5_HOME, q, Tt)
+    rq, rV = cpu_ref.ik_newton_step(synth.UR5_SCREWS, synth.UR5_HOME, q, Tt)
     assert rel_err(Vs, rV).max() < REL
     # dq = pinv(Js) Vs: forward error of the step is bounded by kappa(Js)
     err = np.abs((qo - q) - (rq - q)).max(axis=1) / np.maximum(np.abs(rq - q).max(axis=1), 1e-300)
@@ -260,10 +300,10 @@ def test_ik_solve_loop(mb, port):
 
 # --------------------------------------------------------------------------------------- solvers
 @pytest.mark.parametrize("layout", LAYOUTS)
-def test_linsolve_qr_4x3(mb, port, layout):
+def test_linsolve_qr_4x3(mb, cpu_ref, layout):
     A, b = synth.lstsq_4x3(RAGGED)
     x, st = run(mb, lambda a_, b_, layout: mb.linsolve(mb.QR, 4, 3, a_, b_, layout=layout), layout, A, b)
-    rx, rst = port.linsolve_qr(4, 3, A, b)
+    rx, rst = cpu_ref.linsolve_qr(4, 3, A, b)
     assert np.array_equal(st, rst)
     kappa = np.linalg.cond(A.reshape(-1, 3, 4).transpose(0, 2, 1))
     err = rel_err(x, rx)
@@ -321,11 +361,11 @@ def _svd_checks(A, U, w, V, m, n, rw):
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
-def test_svd_6x6(mb, port, layout):
+def test_svd_6x6(mb, cpu_ref, layout):
     n = 1 << 14
     A = synth.dense(n, 6, 6)
     U, w, V = run(mb, lambda a_, layout: mb.svdcmp(6, 6, a_, layout=layout), layout, A)
-    _, rw, _ = port.svd(6, 6, A)
+    _, rw, _ = cpu_ref.svd(6, 6, A)
     _svd_checks(A, U, w, V, 6, 6, rw)
 
 
@@ -381,11 +421,11 @@ def test_linsolve_svd_6x6(mb, port, layout):
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
-def test_eig_sym_4(mb, port, layout):
+def test_eig_sym_4(mb, cpu_ref, layout):
     n = 1 << 15
     S = synth.symmetric(n, 4)
     d, z = run(mb, lambda s_, layout: mb.eig(4, s_, sorted=True, layout=layout), layout, S)
-    rd, rz = port.eig_sym(4, S, True)
+    rd, rz = cpu_ref.eig_sym(4, S, True)
     scale = np.abs(rd).max(axis=1)
     assert np.all(np.abs(d - rd).max(axis=1) / scale < REL)
     assert np.all(np.diff(d, axis=1) >= 0)  # ascending, like eigsrt (linalg.hpp:1137-1151)
@@ -944,6 +984,112 @@ def test_square_pinv_solve_fast_path_and_fallback(mb, port, fixtures):
     # the two modes agree far inside the parity bar on well-conditioned systems
     well = kappa < 1e3
     assert np.abs(out[True][0][well] - out[False][0][well]).max() < 1e-11
+
+
+def test_graded_triangular_systems_take_the_svd_fallback(mb, port):
+    """I + t triu(ones,1): all partial-pivoting pivots are 1 while cond reaches 3.5e18, where the reference's
+    SVD::solve / pinv drop the smallest singular value (linalg.hpp:889-901, 1211-1227).  The LU shortcut is gated by a
+    rigorous condition bound (lu_cond_bound), so these lanes get the Jacobi SVD answer -- in the default mode, mixed
+    into a batch of ordinary matrices, on both layouts."""
+    from test_math_host import _graded_triangular
+    G = _graded_triangular()
+    A = np.ascontiguousarray(np.vstack([synth.dense(4000, 6, 6, seed=0xE7), G, synth.dense(77, 6, 6, seed=0xE8)]))
+    n = A.shape[0]
+    b = np.ascontiguousarray(synth.dense(n, 6, 1, seed=0xE9))
+    rx, rP = port.linsolve_svd(6, 6, A, b), port.pinv(6, 6, A)
+    kap = np.linalg.cond(A.reshape(n, 6, 6).transpose(0, 2, 1))
+    for layout in LAYOUTS:
+        x = run(mb, lambda a_, b_, layout: mb.linsolve(mb.SVD, 6, 6, a_, b_, layout=layout), layout, A, b)[0]
+        P = run(mb, lambda a_, layout: mb.pinv(6, 6, a_, layout=layout), layout, A)
+        low = kap < 1e13
+        assert np.all(rel_err(x[low], rx[low]) <= 1e-11 * np.maximum(1.0, kap[low]))
+        assert np.all(rel_err(P[low], rP[low]) <= 1e-11 * np.maximum(1.0, kap[low]))
+        trunc = kap > 1e15  # truncation active in the reference: minimum-norm answers of size ~1/t, not ~t^5
+        assert trunc.sum() >= 6
+        assert np.abs(rx[trunc]).max() < 1.0 and np.abs(x[trunc]).max() < 1.0
+        assert np.all(rel_err(x[trunc], rx[trunc]) < 1e-6) and np.all(rel_err(P[trunc], rP[trunc]) < 1e-6)
+
+
+# --------------------------------------------------------------------------------------- several devices
+def _fk_host(host, q, devices):
+    host.set_devices(devices)
+    try:
+        return host.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME).fk_jacobian(q)
+    finally:
+        host.set_devices(None)
+
+
+def test_host_face_device_list(mb):
+    """ppx_cuda_host_set_devices: explicit list = the worker-thread path (exercised with the one device every box has),
+    bad lists are refused, and the result does not depend on the list."""
+    from matrix_b200 import host
+    from matrix_b200._lib import PpxCudaError
+    n = 700_001  # > 5 chunks of 48 MiB / 416 B
+    q = host.pinned_empty((n, 6))
+    q[:] = synth.joint_angles(n, seed=0xD1)
+    T0, J0 = _fk_host(host, q, None)
+    T1, J1 = _fk_host(host, q, [0])
+    assert np.array_equal(T0, T1) and np.array_equal(J0, J1)
+    assert host.get_devices() == []
+    host.set_devices([0])
+    assert host.get_devices() == [0]
+    host.set_devices(None)
+    for bad in ([0, 0], [torch.cuda.device_count()], [-1]):
+        with pytest.raises(PpxCudaError):
+            host.set_devices(bad)
+    assert host.get_devices() == []
+    rates = host.copy_probe(q, "d2h", 0.2)
+    assert len(rates) == 1 and rates[0] > 1.0  # GB/s
+
+
+def test_two_device_host_call_is_bitwise_the_one_device_result(mb, port):
+    """one host call spread over two GPUs (one worker thread per device, chunks from a shared queue) gives
+    bit for bit what one GPU gives -- and both match the oracle."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from matrix_b200 import host
+    n = 1_500_003
+    q = host.pinned_empty((n, 6))
+    q[:] = synth.joint_angles(n, seed=0xD2)
+    T1, J1 = _fk_host(host, q, [0])
+    T2, J2 = _fk_host(host, q, [0, 1])
+    Tb, Jb = _fk_host(host, q, [1])
+    Ta, Ja = _fk_host(host, q, "all")
+    for T, J in ((T2, J2), (Tb, Jb), (Ta, Ja)):
+        assert np.array_equal(T1, T) and np.array_equal(J1, J)
+    m = 1 << 15
+    rT, rJ = port.poe_fk_jacobian(synth.UR5_SCREWS, synth.UR5_HOME, q[-m:])
+    assert rel_err(T2[-m:], rT).max() < REL and rel_err(J2[-m:], rJ).max() < REL
+    # a solver with per-instance status and an optional output left out, over both devices
+    A, b = synth.lstsq_4x3(2_000_001)
+    host.set_devices([0, 1])
+    try:
+        x2, st2 = host.linsolve("QR", 4, 3, A, b)
+    finally:
+        host.set_devices(None)
+    x1, st1 = host.linsolve("QR", 4, 3, A, b)
+    assert np.array_equal(x1, x2) and np.array_equal(st1, st2)
+
+
+def test_two_gpu_shards_concatenate_to_the_one_gpu_result(mb):
+    """the torchrun form of the same property: block r of the batch computed on device r (device-resident, SoA),
+    concatenated, is bitwise the whole batch computed on device 0"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from matrix_b200.shard import shard_ranges
+    n = 1_000_003
+    kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
+    whole = torch.empty((6, n), dtype=torch.float64, device="cuda:0")
+    mb.fill_uniform(whole, 0xD3, 0, -np.pi, np.pi)  # component-major fill: plane k holds counters k*n ..
+    T, Js = kin.fk_jacobian(whole, layout=mb.SOA)
+    parts_T, parts_J = [], []
+    for r, (first, cnt) in enumerate(shard_ranges(n, 2)):
+        with torch.cuda.device(r):
+            qr = whole[:, first:first + cnt].to(f"cuda:{r}").contiguous()
+            Tr, Jr = kin.fk_jacobian(qr, layout=mb.SOA)
+            parts_T.append(Tr.cpu())
+            parts_J.append(Jr.cpu())
+    assert torch.equal(torch.cat(parts_T, dim=1), T.cpu()) and torch.equal(torch.cat(parts_J, dim=1), Js.cpu())
 
 
 # --------------------------------------------------------------------------------------- the bench line itself

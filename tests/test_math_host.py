@@ -111,6 +111,18 @@ def test_device_lu_and_gauss_jordan_on_the_host(mh, port, fixtures):
     assert np.all(errx <= 1e-13 * np.maximum(1.0, kappa))
 
 
+def _graded_triangular():
+    """I + t triu(ones, 1) and its transpose: every partial-pivoting pivot is 1 while cond grows like t^5 (3.5e18 at
+    t = 1e3), so pivot ratios say nothing about the conditioning -- the reference truncates the smallest singular value
+    there (SVD::solve, linalg.hpp:889-901) and an unguarded LU shortcut would return A^-1 b ~ 1e15 instead."""
+    mats = []
+    for t in (1.0, 10.0, 1e2, 3e2, 1e3, 1e4):
+        M = np.eye(6) + t * np.triu(np.ones((6, 6)), 1)
+        for X in (M, M.T, M[::-1, ::-1].copy()):
+            mats.append(X.T.reshape(36))  # column-major record
+    return np.array(mats)
+
+
 def test_square_pinv_solve_paths_on_the_host(mh, port, fixtures):
     """LU fast path vs forced Jacobi SVD vs the oracle's SVD::solve: well-conditioned systems agree to cond * eps on
     both paths; graded condition numbers up to 1e14 cross the pivot test; rank-deficient systems (truncation active in
@@ -123,7 +135,7 @@ def test_square_pinv_solve_paths_on_the_host(mh, port, fixtures):
     sig = np.stack([np.ones(512), np.full(512, 0.7), np.full(512, 0.4), np.full(512, 0.2), np.sqrt(smin), smin], axis=1)
     G = np.einsum("nij,nj,nkj->nik", Q1, sig, Q2).transpose(0, 2, 1).reshape(512, 36)
     edge = fixtures["dense6.A"][192:]
-    A = np.ascontiguousarray(np.vstack([A, G, edge]))
+    A = np.ascontiguousarray(np.vstack([A, G, edge, _graded_triangular()]))
     n = A.shape[0]
     b = np.ascontiguousarray(synth.dense(n, 6, 1, seed=0x82))
     ref = port.linsolve_svd(6, 6, A, b)
