@@ -4,19 +4,25 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--n INSTANCES] [--impl reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
 
-A "step" is one pass of the hot path over one batch of synthetic inputs: one kernel launch over n instances
-per GPU, inputs resident in HBM when the timed region starts.  The headline workload is BASELINE.json's
-configs[1] (UR5 product-of-exponentials forward kinematics + space Jacobian, 16M joint configurations per GPU);
-with N GPUs every rank runs its own 16M-instance shard (weak scaling, no data-path collective: the instances are
-independent).  Rank 0 prints ONE JSON line (see the task contract); extra keys:
+A "step" is one pass of the hot path over one batch of synthetic inputs: one kernel launch over n instances per
+GPU, inputs resident in HBM when the timed region starts.  The headline workload is BASELINE.json's configs[1]
+(UR5 product-of-exponentials forward kinematics + space Jacobian, 16M joint configurations per GPU); with N GPUs
+every rank runs its own 16M-instance shard (weak scaling, no data-path collective: the instances are independent,
+SURVEY.md section 8e).  Rank 0 prints ONE JSON line (the task contract); extra keys:
 
-  roofline      dominant (only) kernel of the step: algorithmic bytes per launch / its CUDA-event duration,
-                against the measured HBM copy bandwidth in MEASURED_PEAKS.json
-  e2e           the same metric through the host ABI (ppx_cuda_host_*): pinned HOST AoS buffers in and out,
-                H2D + kernels + D2H inside the timed region
+  roofline      dominant (only) kernel of the step: algorithmic bytes per launch / its CUDA-event duration, against
+                the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  e2e           the same metric through the host ABI (ppx_cuda_host_*): pinned HOST arrays of reference records in
+                and out, H2D + kernels + D2H inside the timed region.  N = 1: the device of the rank.  N > 1: ONE
+                call of rank 0 spread over all N devices by the library (ppx_cuda_host_set_devices), N x 16M
+                instances -- what a C++ caller of ppx::cuda::batch_* gets; the per-rank form (every rank its own
+                device and buffers, max over ranks) is reported beside it, and `ceiling` holds the aggregate
+                host<->device copy rate the same devices sustain when they only copy (no kernels), measured with
+                all of them running at once
   cpu_baseline  the reference's own CPU routines (oracle/_ref, OpenMP loop over ppx calls) or, if that was not
                 built, the C restatement, on a bounded sample on this box's host cores (N = 1 only)
-  other_workloads  kernel-only throughput + roofline fraction of the other BASELINE configs (N = 1 only)
+  configs       every BASELINE config measured the same way: kernel-only value + roofline (HBM and fp64 fractions),
+                end to end through the host ABI, CPU baseline (N = 1 only); at N > 1 each rank runs its shard
 
 --impl reference times only the CPU implementation (the reference arm).
 """
@@ -34,6 +40,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+ARENA_BYTES = (1 << 24) * 464 + (64 << 20)  # pinned host arena of the end-to-end legs: the headline's 16M x 464 B + slack
 
 
 def env_int(name, default):
@@ -52,30 +59,15 @@ def measured_peaks():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def gpu_local_cpus(device_index):
-    """CPUs of the NUMA node the GPU hangs off (sysfs), or None: pinned buffers allocated by a thread running there land
-    in memory one PCIe hop from the device -- a remote node can cost the host-buffer path most of its PCIe rate."""
-    try:
-        import torch
-        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id  # not available on every torch build
-    except Exception:
-        bdf = None
-    try:
-        if bdf is None:
-            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i",
-                                  str(device_index)], capture_output=True, text=True).stdout.strip()
-            bdf = out.lower().replace("00000000:", "0000:")
-        node = int(open(f"/sys/bus/pci/devices/{str(bdf).lower()}/numa_node").read())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        return cpus or None
-    except Exception:
-        return None
+def config_for(workload, n, world):
+    """the `config` key, identical in both arms (ours and --impl reference) for the same workload, size and N"""
+    from matrix_b200.workloads_meta import META
+    m = META[workload]
+    per = m["bytes"] * n / 1e6
+    return {"workload": workload, "instances_per_gpu": n,
+            "chain": "UR5 (test/lie_test.cpp:187-196)" if m.get("chain") else None,
+            "l2": f"inputs+outputs {per:.0f} MB per step >> 126 MB L2, every byte touched once per step",
+            "parallelism": f"instance-sharded x{world}, no collective"}
 
 
 class ClockSampler:
@@ -131,48 +123,53 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
-def time_cpu(cpu_factory, sample, passes, warm=1):
-    """best-of-`passes` instances/s of the CPU implementation on `sample` instances, all host threads"""
-    from bench_cpu import load_cpu_oracle
+def time_cpu(workload, sample, min_seconds, min_passes=2):
+    """-> cpu_baseline dict: the CPU implementation on `sample` instances, all host threads, passes repeated until
+    `min_seconds` of CPU work have been timed; value = best pass"""
+    from bench_cpu import CPU, NTHREADS, load_cpu_oracle
     oracle, kind = load_cpu_oracle()
-    fn = cpu_factory(oracle, sample)
-    for _ in range(warm):
-        fn()
+    fn = CPU[workload](oracle, sample)
+    fn()  # warm-up: page faults, thread pool
     times = []
-    for _ in range(passes):
+    while len(times) < min_passes or sum(times) < min_seconds:
         t0 = time.perf_counter()
         fn()
         times.append(time.perf_counter() - t0)
-    from bench_cpu import NTHREADS
-    return sample / min(times), sample / statistics.mean(times), times, kind, NTHREADS
+        if len(times) >= 50:
+            break
+    return {"value": sample / min(times), "unit": "instances/s", "cores": NTHREADS, "kind": kind,
+            "mean_value": sample / statistics.mean(times),
+            "sample": f"{sample} instances of {workload} per pass, best of {len(times)} passes ({sum(times):.1f} s of CPU "
+                      "work), OpenMP static loop over the ppx call chain on host arrays of records"}
 
 
 def run_reference_arm(args, rank):
-    """--impl reference: the reference's CPU implementation of the path, bounded sample per step."""
+    """--impl reference: the reference's CPU implementation of the path, every step one pass over the SAME number of
+    instances as a step of the GPU arm on one GPU (the CPU throughput does not depend on the batch size; N ranks of the
+    GPU arm each run that many)."""
     from matrix_b200.workloads_meta import META
     if rank != 0:
         return
     from bench_cpu import CPU, NTHREADS, load_cpu_oracle
     meta = META[args.workload]
-    sample = args.n if args.n else meta["cpu_sample"]
+    n = args.n if args.n else meta["n"]
     oracle, kind = load_cpu_oracle()
-    fn = CPU[args.workload](oracle, sample)
+    fn = CPU[args.workload](oracle, n)
     for _ in range(args.warmup):
         fn()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         fn()
     dt = time.perf_counter() - t0
-    value = sample * args.steps / dt
-    desc = f"{sample} instances of {args.workload} per step (OpenMP static loop over the ppx call chain, AoS host arrays)"
+    value = n * args.steps / dt
+    desc = (f"{n} instances of {args.workload} per step, {args.steps} steps ({dt:.1f} s of CPU work): OpenMP static loop "
+            "over the ppx call chain (oracle/_ref: the unmodified reference headers), host arrays of records")
     print(json.dumps({
         "impl": "reference", "metric": "instances/sec", "value": value, "unit": "instances/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "instances_per_step": sample, "layout": "aos (host)",
-                   "device": "cpu"},
-        "cpu_baseline": {"value": value, "unit": "instances/s", "cores": NTHREADS, "kind": kind,
-                         "sample": desc},
+        "config": config_for(args.workload, n, max(args.gpus, 1)),
+        "cpu_baseline": {"value": value, "unit": "instances/s", "cores": NTHREADS, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -186,13 +183,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--n", type=int, default=0, help="instances per GPU per step (default: the BASELINE size)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--no-others", action="store_true", help="skip the per-config table")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--only", default="", help="comma-separated workloads of the per-config table")
     ap.add_argument("--layout", choices=["soa", "aos"], default="soa", help="record layout of --all-ops")
     ap.add_argument("--all-ops", action="store_true",
-                    help="time every batched entry point (kernel only, SoA) next to its CPU reference; one JSON line")
+                    help="time every batched entry point (kernel only) next to its CPU reference; one JSON line")
     args = ap.parse_args()
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -213,13 +211,21 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
 
-    from matrix_b200 import _lib
-    from matrix_b200.workloads import WORKLOADS
+    from matrix_b200 import _lib, host
+    from matrix_b200.workloads import WORKLOADS, Arena
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    host_pg = dist.new_group(backend="gloo") if world > 1 else None
+
+    def host_barrier():
+        """CPU-side barrier (gloo): unlike an NCCL barrier it parks no kernel on the GPUs while the ranks wait"""
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_pg)
 
     def max_over_ranks(x):
         if world > 1:
@@ -228,8 +234,11 @@ def main():
             return float(t.item())
         return x
 
+    def min_over_ranks(x):
+        return -max_over_ranks(-x)
+
     def time_steps(w, steps, warmup):
-        """-> (ms for all `steps` steps, CUDA events on the launching stream, max over ranks; per-step ms list)"""
+        """-> (ms for all `steps` steps: CUDA events on the launching stream, max over ranks; per-step ms list)"""
         for _ in range(warmup):
             w.step()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
@@ -244,192 +253,290 @@ def main():
 
     hbm_peak, peak_src = measured_peaks()
     if args.all_ops:
-        # one line per C-ABI entry point that is not already a BASELINE workload: kernel-only inst/s and GB/s on
-        # device-resident SoA data, with the CPU reference (all host threads, 2^20-instance sample) beside it
-        import time as _t
-        from matrix_b200 import ops_table
-        from bench_cpu import NTHREADS, cpu_op, load_cpu_oracle
-        oracle, kind = load_cpu_oracle()
-        rows = []
-        from matrix_b200 import batch as _mb
-        op_layout = _mb.AOS if args.layout == "aos" else _mb.SOA
-        for op in ops_table.make_ops(op_layout):
-            op.setup(device)
-            for _ in range(3):
-                op.step()
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-            torch.cuda.synchronize()
-            ev[0].record()
-            for i in range(5):
-                op.step()
-                ev[i + 1].record()
-            torch.cuda.synchronize()
-            ms = statistics.mean(ev[i].elapsed_time(ev[i + 1]) for i in range(5))
-            sample = 1 << 20 if "ik_" not in op.name else 1 << 18
-            fn = cpu_op(op.name, oracle, sample)
-            fn()
-            t0 = _t.perf_counter()
-            fn()
-            cpu_s = _t.perf_counter() - t0
-            gbs = op.n * op.bytes / (ms * 1e-3) / 1e9
-            rows.append({"op": op.name, "reference": op.ref, "instances": op.n, "kernel_ms": ms,
-                         "value": op.n / (ms * 1e-3), "unit": "instances/s", "algorithmic_bytes_per_instance": op.bytes,
-                         "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "touched_bytes_per_instance": op.touched,
-                         "hbm_frac_touched": gbs / hbm_peak * op.touched / op.bytes,
-                         "cpu_value": sample / cpu_s, "cpu_cores": NTHREADS,
-                         "cpu_kind": kind})
-            op.step = None
-            torch.cuda.empty_cache()
-        print(json.dumps({"all_ops": rows, "hbm_peak_gbs": hbm_peak, "layout": f"{args.layout} (device resident)",
-                          "dtype": "f64"}))
+        all_ops(args, device, hbm_peak)
         return
-    cls = WORKLOADS[args.workload]
-    n = args.n or cls.n_default
-    w = cls(n, device, first=rank * n)
-    w.setup()
-    torch.cuda.synchronize()
 
-    with ClockSampler(local) as clocks:
-        launches0 = _lib.launch_count()
-        total_ms, per_step = time_steps(w, args.steps, args.warmup)
-        launches = _lib.launch_count() - launches0 - args.warmup
-        # keep the sampler alive for a minimum window so short runs still get a few samples under load
-        t_end = time.time() + max(0.0, 1.0 - total_ms / 1e3)
-        while time.time() < t_end:
-            w.step()
-        torch.cuda.synchronize()
-    value = world * n * args.steps / (total_ms * 1e-3)
-    kernel_ms = statistics.mean(per_step)
-    achieved = n * cls.bytes_per_instance() / (kernel_ms * 1e-3) / 1e9
-    # per-launch DRAM traffic and per-instance fp64 flop counts measured once by ncu on the same seeded workload
-    # (tools/make_counters.py -> profiles/counters.json); null when this n was not profiled
+    # per-launch DRAM traffic and per-instance fp64 counts measured by ncu on the same seeded workloads
+    # (tools/make_counters.py -> profiles/counters.json); not re-measured in this run
     try:
         with open(os.path.join(ROOT, "profiles", "counters.json")) as f:
             counters = json.load(f)
     except Exception:
         counters = {}
-    c_head = counters.get(args.workload, {})
-    traffic = c_head.get("dram_bytes_per_launch") if c_head.get("instances") == n else None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": cls.kernel,
-                "kernel_ms": kernel_ms, "algorithmic_bytes_per_instance": cls.bytes_per_instance(),
-                "instances_per_launch": n}
-
-    # ---- e2e: host AoS buffers through the host ABI, copies inside the timed region -----------------------------
-    e2e = None
-    if not args.no_e2e and hasattr(w, "host_setup"):
-        try:
-            import psutil
-            avail = psutil.virtual_memory().available
-        except Exception:
-            avail = 64 << 30
-        per_inst = cls.bytes_per_instance()
-        n_e2e = n
-        while n_e2e * per_inst * 3 * max(world, 1) > avail and n_e2e > (1 << 18):
-            n_e2e //= 2
-        del w.T, w.Js  # free device outputs of the kernel-only leg
-        torch.cuda.empty_cache()
-        all_cpus = os.sched_getaffinity(0)
-        near = gpu_local_cpus(local)
-        if near:
-            os.sched_setaffinity(0, near)  # allocate (first-touch) the pinned buffers on the GPU's NUMA node
-        h2d, d2h = w.host_setup(n_e2e)
-        # raw pinned-copy rates of this box: the ceiling of any host-buffer path
-        probe_h = torch.empty(1 << 28, dtype=torch.uint8, pin_memory=True)
-        probe_d = torch.empty(1 << 28, dtype=torch.uint8, device=device)
-        pcie = {}
-        for name, (dst, src) in {"h2d": (probe_d, probe_h), "d2h": (probe_h, probe_d)}.items():
-            dst.copy_(src, non_blocking=True)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(4):
-                dst.copy_(src, non_blocking=True)
-            torch.cuda.synchronize()
-            pcie[name] = 4 * probe_h.numel() / (time.perf_counter() - t0) / 1e9
-        del probe_h, probe_d
-        w.host_step()  # warm-up (page-locks, stream-ordered pool growth)
-        barrier()
-        t0 = time.perf_counter()
-        e2e_steps_ms = []
-        for _ in range(args.e2e_steps):
-            ts = time.perf_counter()
-            loss = w.host_step()  # blocking: returns when the outputs are in host memory
-            e2e_steps_ms.append((time.perf_counter() - ts) * 1e3)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            dist.barrier()
-        dt = max_over_ranks(dt)
-        e2e = {"value": world * n_e2e * args.e2e_steps / dt, "unit": "instances/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "instances_per_step": n_e2e, "steps": args.e2e_steps,
-               "ms_per_step": dt / args.e2e_steps * 1e3, "api": "ppx_cuda_host_poe_fk_jacobian (pinned host AoS)",
-               "pcie_gbs": (h2d + d2h) * args.e2e_steps / dt / 1e9, "pcie_h2d_gbs_measured": pcie["h2d"],
-               "pcie_d2h_gbs_measured": pcie["d2h"], "result_probe": loss}
-        e2e["numa_bound"] = bool(near)
-        e2e["step_ms"] = {"min": min(e2e_steps_ms), "median": statistics.median(e2e_steps_ms), "max": max(e2e_steps_ms)}
-        os.sched_setaffinity(0, all_cpus)
-        for k in ("hq", "hT", "hJ"):
-            if hasattr(w, k):
-                delattr(w, k)
-    del w
-    torch.cuda.empty_cache()
-
-    # ---- secondary workloads + fp64 peak + CPU baseline (rank 0 of a single-GPU run only) -----------------------
-    others, fp64_peak, cpu = [], None, None
-    if world == 1 and rank == 0:
+    fp64_peak = None
+    if rank == 0:
         from matrix_b200 import batch as mb
         fp64_peak = mb.fp64_peak_tflops()
-        if not args.no_others:
-            for name, c in WORKLOADS.items():
-                if name == args.workload:
-                    continue
-                try:
-                    ww = c(c.n_default, device)
-                    ww.setup()
-                    ms, per = time_steps(ww, 5, 3)
-                    k_ms = statistics.mean(per)
-                    gbs = c.n_default * c.bytes_per_instance() / (k_ms * 1e-3) / 1e9
-                    entry = {"workload": name, "instances": c.n_default, "value": c.n_default / (k_ms * 1e-3),
-                             "unit": "instances/s", "kernel_ms": k_ms, "hbm_gbs": gbs,
-                             "hbm_frac": gbs / hbm_peak, "expected_bound": c.bound,
-                             "algorithmic_bytes_per_instance": c.bytes_per_instance()}
-                    cc = counters.get(name, {})
-                    if cc.get("fp64_flops_per_instance") and fp64_peak:
-                        tf = cc["fp64_flops_per_instance"] * entry["value"] / 1e12
-                        entry.update({"fp64_flops_per_instance_ncu": cc["fp64_flops_per_instance"],
-                                      "fp64_tflops": tf, "fp64_frac_of_measured_peak": tf / fp64_peak,
-                                      "fp64_pipe_pct_ncu": cc.get("fp64_pipe_pct")})
-                    others.append(entry)
-                    del ww
-                    torch.cuda.empty_cache()
-                except Exception as e:  # report, never hide
-                    others.append({"workload": name, "error": repr(e)})
-        if not args.no_cpu:
-            from bench_cpu import CPU
-            meta = META[args.workload]
-            best, mean, times, kind, cores = time_cpu(CPU[args.workload], meta["cpu_sample"], passes=3)
-            cpu = {"value": best, "unit": "instances/s", "cores": cores, "kind": kind,
-                   "sample": f"{meta['cpu_sample']} instances of {args.workload}, best of 3 passes "
-                             f"({sum(times):.1f} s of CPU work), OpenMP static loop over the ppx call chain"}
+    fp64_peak = max_over_ranks(fp64_peak or 0.0) or None  # rank 0's probe, shared with everybody
+    arena = None
+
+    def roofline_of(cls, name, n_launch, kernel_ms):
+        """HBM: algorithmic bytes / launch time vs the measured copy peak.  fp64: ncu-counted flops per instance
+        (2 per DFMA, 1 per DADD / DMUL, profiles/counters.json) x instances/s vs the DFMA probe of this run."""
+        gbs = n_launch * cls.bytes_per_instance() / (kernel_ms * 1e-3) / 1e9
+        r = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+             "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "peak_source": peak_src, "kernel": cls.kernel,
+             "kernel_ms": kernel_ms, "algorithmic_bytes_per_instance": cls.bytes_per_instance(),
+             "instances_per_launch": n_launch}
+        c = counters.get(name) or counters.get(META[name].get("counters_as", ""), {})
+        r["traffic"] = c.get("dram_bytes_per_launch") if c.get("instances") == n_launch else None
+        r["traffic_source"] = (f"ncu --set full capture of the same kernel and batch size, {c.get('report', '?')} "
+                               "(profiles/counters.json); not re-measured in this run") if r["traffic"] else None
+        if c.get("fp64_flops_per_instance") and fp64_peak:
+            tf = c["fp64_flops_per_instance"] * n_launch / (kernel_ms * 1e-3) / 1e12
+            r.update({"fp64_tflops": tf, "fp64_frac": tf / fp64_peak, "fp64_peak_tflops": fp64_peak,
+                      "fp64_flops_per_instance_ncu": c["fp64_flops_per_instance"],
+                      "fp64_counters_from": c.get("report"), "fp64_pipe_pct_ncu": c.get("fp64_pipe_pct")})
+            if cls.bound.startswith("fp64") and tf / fp64_peak > r["hbm_frac"]:
+                r.update({"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                          "peak_source": "measured in this run (ppx_cuda_fp64_peak_probe: dependent-free DFMA on every SM)"})
+        return r
+
+    def e2e_leg(w, cls, n, steps):
+        """the same step through the host ABI on this rank's device: pinned host arrays, copies inside the timed region;
+        every rank runs its own shard at once, time = max over ranks"""
+        nonlocal arena
+        if arena is None:
+            arena = Arena(ARENA_BYTES)
+        arena.reset()
+        n_e2e = n
+        while n_e2e * cls.bytes_per_instance() + (1 << 20) > ARENA_BYTES and n_e2e > 1024:
+            n_e2e //= 2  # e.g. svd_6x6: 912 B per instance, 8M instances per call instead of 16M
+        h2d, d2h = w.host_setup(n_e2e, arena)
+        w.host_step()  # warm-up (stream-ordered pool growth)
+        barrier()
+        t0 = time.perf_counter()
+        per = []
+        for _ in range(steps):
+            ts = time.perf_counter()
+            probe = w.host_step()  # blocking: returns when the outputs are in host memory
+            per.append((time.perf_counter() - ts) * 1e3)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        w.host_release()
+        return {"value": world * n_e2e * steps / dt, "unit": "instances/s", "h2d_bytes_per_step": h2d * world,
+                "d2h_bytes_per_step": d2h * world, "instances_per_step": n_e2e * world, "steps": steps,
+                "ms_per_step": dt / steps * 1e3, "api": f"{cls.host_api} (pinned host arrays of records)",
+                "mode": "one call per rank on its own device, max over ranks" if world > 1 else "one call, one device",
+                "pcie_gbs": (h2d + d2h) * world * steps / dt / 1e9, "result_probe": probe,
+                "step_ms": {"min": min(per), "median": statistics.median(per), "max": max(per)}}
+
+    def run_config(name, n, steps, warmup, cpu_seconds, e2e_steps, headline=False, sampler=None):
+        cls = WORKLOADS[name]
+        w = cls(n, device, first=rank * n * getattr(cls, "NBUF", 1))
+        w.setup()
+        torch.cuda.synchronize()
+        per_step_launches = getattr(w, "launches_per_step", 1)  # > 1: a CUDA graph of that many launches per step
+        per_step_instances = getattr(w, "instances_per_step", n)
+        if sampler is not None:
+            sampler.__enter__()
+        launches0 = _lib.launch_count()
+        total_ms, per = time_steps(w, steps, warmup)
+        counted = _lib.launch_count() - launches0  # launches the library itself issued (graph replays are not seen)
+        launches = steps * per_step_launches if per_step_launches > 1 else counted - warmup
+        if sampler is not None:
+            # keep the sampler alive for a minimum window so short runs still get a few samples under load
+            t_end = time.time() + max(0.0, 1.0 - total_ms / 1e3)
+            while time.time() < t_end:
+                w.step()
+            torch.cuda.synchronize()
+            sampler.__exit__(None, None, None)
+        kernel_ms = max_over_ranks(statistics.mean(per)) / per_step_launches
+        entry = {"workload": name, "instances_per_gpu": per_step_instances, "n_gpus": world,
+                 "value": world * per_step_instances * steps / (total_ms * 1e-3), "unit": "instances/s",
+                 "steps": steps, "ms_per_step": total_ms / steps, "gpu_launches": int(launches),
+                 "roofline": roofline_of(cls, name, n, kernel_ms),
+                 "step_ms": {"min": min(per), "median": statistics.median(per), "max": max(per)}}
+        keep = (w, total_ms, per, launches) if headline else None
+        e2e = None
+        if not args.no_e2e and cls.host_api:
+            w.free_outputs()
+            torch.cuda.empty_cache()
+            e2e = e2e_leg(w, cls, n, e2e_steps)
+        entry["e2e"] = e2e
+        cpu = None
+        if world == 1 and rank == 0 and not args.no_cpu:
+            cpu = time_cpu(name, META[name]["cpu_sample"], cpu_seconds)
+        entry["cpu_baseline"] = cpu
+        if not headline:
+            del w
+            torch.cuda.empty_cache()
+        return entry, keep
+
+    # ---- headline ------------------------------------------------------------------------------------------------
+    cls = WORKLOADS[args.workload]
+    n = args.n or cls.n_default
+    clocks = ClockSampler(local)  # nvidia-smi samples during the timed kernel region of the headline only
+    head, (w, total_ms, per_step, launches) = run_config(args.workload, n, args.steps, args.warmup, 12.0,
+                                                         args.e2e_steps, headline=True, sampler=clocks)
+    e2e = head["e2e"]
+
+    # ---- N > 1: the host-buffer face of the library itself over all N devices, one call from rank 0 ---------------
+    if world > 1 and e2e is not None:
+        per_rank = dict(e2e)
+        arena = None  # every rank gives its pinned arena back before rank 0 page-locks the big one
+        del w
+        torch.cuda.empty_cache()
+        host_barrier()
+        multi = None
+        if rank == 0:
+            try:
+                import psutil
+                avail = psutil.virtual_memory().available
+            except Exception:
+                avail = 64 << 30
+            n_all = n * world
+            while n_all * cls.bytes_per_instance() * 1.25 > avail and n_all > (1 << 20):
+                n_all //= 2
+            try:
+                multi = multi_device_e2e(cls, n, n_all, world, args.e2e_steps, device, host, Arena)
+            except Exception as e:  # report, never hide: the per-rank number stays the e2e of the line
+                per_rank["multi_device_error"] = repr(e)
+        host_barrier()
+        if rank == 0 and multi is not None:
+            e2e = multi
+            e2e["per_rank"] = {k: per_rank[k] for k in ("value", "ms_per_step", "pcie_gbs", "mode", "instances_per_step")}
+    elif e2e is not None and rank == 0:
+        # the ceiling of the one-device host path: what this device's link carries when it only copies
+        arena.reset()
+        buf = arena.take((1 << 30,), "uint8")
+        rates = {d: host.copy_probe(buf, d, 0.5)[0] for d in ("h2d", "d2h", "both")}
+        e2e["ceiling"] = {"probe": "ppx_cuda_host_copy_probe: the same pinned arena, 48 MiB pieces, no kernels, 0.5 s each",
+                          "h2d_gbs": rates["h2d"], "d2h_gbs": rates["d2h"], "both_gbs": rates["both"],
+                          "pipeline_gbs": e2e["pcie_gbs"],
+                          "frac_of_d2h": (e2e["d2h_bytes_per_step"] / (e2e["ms_per_step"] * 1e-3) / 1e9) / rates["d2h"]}
+
+    # ---- every other BASELINE config, measured the same way --------------------------------------------------------
+    table = [head]
+    if not args.no_others:
+        want = [s for s in args.only.split(",") if s] or [k for k in WORKLOADS if k != args.workload]
+        for name in want:
+            try:
+                entry, _ = run_config(name, WORKLOADS[name].n_default, 5, 3, 3.0, 3)
+                table.append(entry)
+            except Exception as e:  # report, never hide
+                table.append({"workload": name, "error": repr(e)})
+                torch.cuda.empty_cache()
 
     if rank == 0:
+        value = world * n * args.steps / (total_ms * 1e-3)
+        for t in table:  # GPU / CPU ratios where both legs exist (N = 1)
+            c = t.get("cpu_baseline")
+            if c:
+                t["kernel_vs_cpu"] = t["value"] / c["value"]
+                if t.get("e2e"):
+                    t["e2e_vs_cpu"] = t["e2e"]["value"] / c["value"]
         out = {
             "metric": "instances/sec", "value": value, "unit": "instances/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "instances_per_gpu": n, "layout": f"{cls.layout} (device resident)",
-                       "chain": "UR5 (test/lie_test.cpp:187-196)" if "ur5" in args.workload or "ik" in args.workload or "inverse" in args.workload
-                       else None,
-                       "l2": f"inputs+outputs {n * cls.bytes_per_instance() / 1e6:.0f} MB per step >> 126 MB L2, "
-                             "evict-first loads/stores", "parallelism": f"instance-sharded x{world}, no collective"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks.summary(), "fp64_peak_tflops_measured": fp64_peak,
+            "config": config_for(args.workload, n, world),
+            "layout": f"{cls.layout} (device resident)",
+            "roofline": head["roofline"], "cpu_baseline": head["cpu_baseline"], "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "fp64_peak_tflops_measured": fp64_peak,
             "step_ms": {"min": min(per_step), "median": statistics.median(per_step), "max": max(per_step)},
-            "other_workloads": others,
+            "configs": table,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_device_e2e(cls, n_per_gpu, n_all, world, steps, device, host, Arena):
+    """rank 0 only: ONE ppx_cuda_host_* call over `world` devices on n_all instances of pinned host records, and the
+    aggregate copy ceiling of the same devices (all copying at once, no kernels)"""
+    import statistics as st
+    import torch
+    t_pin = time.perf_counter()
+    big = Arena(n_all * cls.bytes_per_instance() + (64 << 20))
+    t_pin = time.perf_counter() - t_pin
+    # the inputs of all shards: regenerated shard by shard on this device (counter-based generator), copied to the host
+    hq, w, first = None, None, 0
+    while first < n_all:
+        cnt = min(n_per_gpu, n_all - first)
+        w = cls(cnt, device, first=first)
+        w.setup()
+        w.free_outputs()
+        ins = w.host_inputs()
+        if hq is None:
+            hq = [big.take((n_all, t.shape[1])) for t in ins]
+        for a, t in zip(hq, ins):
+            torch.from_numpy(a[first:first + cnt]).copy_(t)
+        torch.cuda.synchronize()
+        del ins
+        first += cnt
+    torch.cuda.empty_cache()
+    h_out = [big.take((n_all, wd) if wd > 1 else (n_all,), dt) for wd, dt in cls.host_out]
+    h2d, d2h = sum(a.nbytes for a in hq), sum(a.nbytes for a in h_out)
+    host.set_devices(list(range(world)))
+    try:
+        w.host_call(n_all, hq, h_out)  # warm-up: contexts, streams and scratch pools of all devices
+        per = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ts = time.perf_counter()
+            w.host_call(n_all, hq, h_out)
+            per.append((time.perf_counter() - ts) * 1e3)
+        dt = time.perf_counter() - t0
+        probe = float(h_out[0].reshape(n_all, -1)[-1, -1])
+        rates = {d: host.copy_probe(big.buf, d, 1.0) for d in ("d2h", "both")}
+    finally:
+        host.set_devices(None)
+    pipeline_gbs = (h2d + d2h) * steps / dt / 1e9
+    d2h_gbs = d2h * steps / dt / 1e9
+    return {"value": n_all * steps / dt, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "instances_per_step": n_all, "steps": steps, "ms_per_step": dt / steps * 1e3,
+            "api": f"{cls.host_api} (pinned host arrays of records)",
+            "mode": f"ONE call from one process spread over {world} devices by the library (worker thread per device, "
+                    "chunks from a shared queue)",
+            "pcie_gbs": pipeline_gbs, "result_probe": probe, "pin_seconds": t_pin,
+            "step_ms": {"min": min(per), "median": st.median(per), "max": max(per)},
+            "ceiling": {"probe": f"ppx_cuda_host_copy_probe: all {world} devices copying at once through the same pinned "
+                                 "buffer, 48 MiB pieces, no kernels, 1 s per direction",
+                        "d2h_gbs_per_device": rates["d2h"], "d2h_gbs_aggregate": sum(rates["d2h"]),
+                        "both_gbs_per_device": rates["both"], "both_gbs_aggregate": sum(rates["both"]),
+                        "pipeline_gbs": pipeline_gbs, "pipeline_d2h_gbs": d2h_gbs,
+                        "frac_of_d2h_aggregate": d2h_gbs / max(sum(rates["d2h"]), 1e-9)}}
+
+
+def all_ops(args, device, hbm_peak):
+    """one line per C-ABI entry point that is not already a BASELINE workload: kernel-only inst/s and GB/s on
+    device-resident data, with the CPU reference (all host threads, 2^20-instance sample) beside it"""
+    import time as _t
+    import torch
+    from matrix_b200 import batch as _mb, ops_table
+    from bench_cpu import NTHREADS, cpu_op, load_cpu_oracle
+    oracle, kind = load_cpu_oracle()
+    rows = []
+    op_layout = _mb.AOS if args.layout == "aos" else _mb.SOA
+    for op in ops_table.make_ops(op_layout):
+        op.setup(device)
+        for _ in range(3):
+            op.step()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        torch.cuda.synchronize()
+        ev[0].record()
+        for i in range(5):
+            op.step()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ms = statistics.mean(ev[i].elapsed_time(ev[i + 1]) for i in range(5))
+        sample = 1 << 20 if "ik_" not in op.name else 1 << 18
+        fn = cpu_op(op.name, oracle, sample)
+        fn()
+        t0 = _t.perf_counter()
+        fn()
+        cpu_s = _t.perf_counter() - t0
+        gbs = op.n * op.bytes / (ms * 1e-3) / 1e9
+        rows.append({"op": op.name, "reference": op.ref, "instances": op.n, "kernel_ms": ms,
+                     "value": op.n / (ms * 1e-3), "unit": "instances/s", "algorithmic_bytes_per_instance": op.bytes,
+                     "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "touched_bytes_per_instance": op.touched,
+                     "hbm_frac_touched": gbs / hbm_peak * op.touched / op.bytes,
+                     "cpu_value": sample / cpu_s, "cpu_cores": NTHREADS, "cpu_kind": kind})
+        op.step = None
+        torch.cuda.empty_cache()
+    print(json.dumps({"all_ops": rows, "hbm_peak_gbs": hbm_peak, "layout": f"{args.layout} (device resident)",
+                      "dtype": "f64"}))
 
 
 if __name__ == "__main__":

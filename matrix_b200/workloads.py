@@ -2,14 +2,18 @@
 
 Each workload knows how to build its synthetic inputs on the device (from the counter-based generator of
 matrix_b200.synth, so any shard can be regenerated anywhere), how to run one hot-path step on device-resident
-SoA data, how to run the same step through the host ABI on host AoS buffers, and how many bytes an instance
-moves at minimum (the dense reference record sizes).
+data (one kernel launch), how to run the same step through the host ABI on pinned host arrays of reference
+records (ppx_cuda_host_*: H2D + kernel + D2H per call), and how many bytes an instance moves at minimum (the
+dense reference record sizes).
 """
+import ctypes as C
+
 import numpy as np
 import torch
 
 from . import batch as mb
 from . import synth
+from ._lib import check, lib
 from .workloads_meta import HEADLINE, META  # noqa: F401
 
 
@@ -20,6 +24,36 @@ def _device_records(n, width, seed, first, lo, hi, device):
     return t
 
 
+def _vp(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _hp(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Arena:
+    """One pinned host block (ppx_cuda_malloc_host) that the end-to-end legs of all workloads carve their arrays
+    from, so that the bench page-locks host memory once."""
+
+    def __init__(self, nbytes):
+        from . import host
+        self.buf = host.pinned_empty((int(nbytes),), np.uint8)
+        self.reset()
+
+    def reset(self):
+        self.off = 0
+
+    def take(self, shape, dtype=np.float64):
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        start = (self.off + 4095) // 4096 * 4096
+        if start + nbytes > self.buf.size:
+            raise MemoryError("pinned arena too small")
+        self.off = start + nbytes
+        return self.buf[start:start + nbytes].view(dtype).reshape(shape)
+
+
 class Workload:
     name = ""
     kernel = ""  # the kernel one step() launches
@@ -28,6 +62,8 @@ class Workload:
     bytes_in = 0      # algorithmic bytes per instance
     bytes_out = 0
     bound = "hbm"
+    host_api = ""     # the ppx_cuda_host_* entry point of the end-to-end leg
+    host_out = ()     # ((width, numpy dtype), ...) of the host-leg outputs
 
     def __init__(self, n, device, first=0):
         self.n, self.device, self.first = n, device, first
@@ -36,6 +72,35 @@ class Workload:
     def bytes_per_instance(cls):
         return cls.bytes_in + cls.bytes_out
 
+    # ---- host ABI leg: pinned host arrays of dense records in and out ---------------------------------------
+    def host_inputs(self):
+        """-> list of (n, width) float64 DEVICE tensors in record layout (the leg copies them to the host once)"""
+        raise NotImplementedError
+
+    def host_call(self, n, ins, outs):
+        raise NotImplementedError
+
+    def host_setup(self, n, arena):
+        """inputs of the first n instances to pinned host arrays, pinned outputs; -> (h2d bytes, d2h bytes) per step"""
+        srcs = self.host_inputs()
+        self.h_in = []
+        for t in srcs:
+            a = arena.take((n, t.shape[1]))
+            torch.from_numpy(a).copy_(t[:n])
+            self.h_in.append(a)
+        torch.cuda.synchronize()
+        self.h_out = [arena.take((n, w) if w > 1 else (n,), dt) for w, dt in self.host_out]
+        self.h_n = n
+        return sum(a.nbytes for a in self.h_in), sum(a.nbytes for a in self.h_out)
+
+    def host_step(self):
+        """one blocking call of the host ABI; -> a value read from the result (proof the outputs arrived)"""
+        self.host_call(self.h_n, self.h_in, self.h_out)
+        return float(self.h_out[0].reshape(self.h_n, -1)[-1, -1])
+
+    def host_release(self):
+        self.h_in = self.h_out = None
+
 
 class Ur5FkJacobian(Workload):
     """config 2: UR5 product-of-exponentials forward kinematics + space Jacobian"""
@@ -43,10 +108,12 @@ class Ur5FkJacobian(Workload):
     kernel = "batch_kernel_pf<SOA, OpFkJacobian<6, true, true>>"
     n_default = 1 << 24
     bytes_in, bytes_out = 48, 128 + 288
+    host_api = "ppx_cuda_host_poe_fk_jacobian"
+    host_out = ((16, np.float64), (36, np.float64))
 
     def setup(self):
         self.kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
-        q = _device_records(self.n, 6, synth.SEEDS[self.name], self.first, -np.pi, np.pi, self.device)
+        q = _device_records(self.n, 6, synth.SEEDS["ur5_fk_jacobian"], self.first, -np.pi, np.pi, self.device)
         self.q = mb.to_soa(q)
         del q
         self.T = torch.empty((16, self.n), dtype=torch.float64, device=self.device)
@@ -55,20 +122,15 @@ class Ur5FkJacobian(Workload):
     def step(self):
         self.kin.fk_jacobian(self.q, layout=mb.SOA, out_T=self.T, out_Js=self.Js)
 
-    # host ABI
-    def host_setup(self, n):
-        from . import host
-        self.hkin = host.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
-        self.hq = host.pinned_empty((n, 6))
-        self.hq[:] = synth.joint_angles(n, first=self.first)
-        self.hT = host.pinned_empty((n, 16))
-        self.hJ = host.pinned_empty((n, 36))
-        return self.hq.nbytes, self.hT.nbytes + self.hJ.nbytes
+    def free_outputs(self):
+        self.T = self.Js = None
 
-    def host_step(self):
-        self.hkin.fk_jacobian(self.hq, out_T=self.hT, out_Js=self.hJ)
-        return float(self.hT[-1, 12])
+    def host_inputs(self):
+        return [mb.to_aos(self.q) if self.layout == "soa" else self.q]
 
+    def host_call(self, n, ins, outs):
+        check(lib.ppx_cuda_host_poe_fk_jacobian(_hp(self.kin.screws), _hp(self.kin.home), 6, _hp(ins[0]), _hp(outs[0]),
+                                                _hp(outs[1]), n))
 
 
 class Ur5FkJacobianAoS(Ur5FkJacobian):
@@ -87,29 +149,76 @@ class Ur5FkJacobianAoS(Ur5FkJacobian):
         self.kin.fk_jacobian(self.q, layout=mb.AOS, out_T=self.T, out_Js=self.Js)
 
 
+def _twists_soa(n, first, device):
+    r = _device_records(n, 6, synth.SEEDS["se3_exp_log"], first, 0.0, 1.0, device)
+    z = 2.0 * r[:, 0] - 1.0
+    ph = 2.0 * np.pi * r[:, 1]
+    s = torch.sqrt(torch.clamp(1.0 - z * z, min=0.0))
+    th = 0.05 + (np.pi - 0.1) * r[:, 2]
+    xi = torch.empty((6, n), dtype=torch.float64, device=device)
+    xi[0], xi[1], xi[2] = th * s * torch.cos(ph), th * s * torch.sin(ph), th * z
+    xi[3:] = (2.0 * r[:, 3:] - 1.0).t()
+    return xi
+
+
 class Se3ExpLog(Workload):
-    """config 1: se3::exp -> SE3::log round trip, fused"""
+    """config 1 at an HBM-resident size (64M twists): se3::exp -> SE3::log round trip, fused"""
     name = "se3_exp_log"
     kernel = "batch_kernel_pf<SOA, OpSe3ExpLog>"
-    n_default = 1 << 26  # the 1M-instance case of BASELINE fits in L2; 64M is the HBM-resident size
+    n_default = 1 << 26
     bytes_in, bytes_out = 48, 48
+    host_api = "ppx_cuda_host_se3_exp_log"
+    host_out = ((6, np.float64),)
 
     def setup(self):
-        r = _device_records(self.n, 6, synth.SEEDS[self.name], self.first, 0.0, 1.0, self.device)
-        z = 2.0 * r[:, 0] - 1.0
-        ph = 2.0 * np.pi * r[:, 1]
-        s = torch.sqrt(torch.clamp(1.0 - z * z, min=0.0))
-        th = 0.05 + (np.pi - 0.1) * r[:, 2]
-        xi = torch.empty((6, self.n), dtype=torch.float64, device=self.device)
-        xi[0], xi[1], xi[2] = th * s * torch.cos(ph), th * s * torch.sin(ph), th * z
-        xi[3:] = (2.0 * r[:, 3:] - 1.0).t()
-        self.xi = xi
-        del r
-        self.out = torch.empty_like(xi)
+        self.xi = _twists_soa(self.n, self.first, self.device)
+        self.out = torch.empty_like(self.xi)
 
     def step(self):
         mb.se3_exp_log(self.xi, layout=mb.SOA, out=self.out)
 
+    def free_outputs(self):
+        self.out = None
+
+    def host_inputs(self):
+        return [mb.to_aos(self.xi)]
+
+    def host_call(self, n, ins, outs):
+        check(lib.ppx_cuda_host_se3_exp_log(_hp(ins[0]), _hp(outs[0]), n))
+
+
+class Se3ExpLog1M(Se3ExpLog):
+    """config 1 at its stated size, 1M twists (96 MB per launch: it would sit in the 126 MB L2), over NBUF = 8 rotating
+    buffer sets (768 MB touched per rotation) so that every launch streams from and to HBM.  A launch lasts ~17 us, the
+    scale of a launch from Python, so the rotation is captured once in a CUDA graph and step() replays it: one step =
+    NBUF launches over NBUF x 1M instances."""
+    name = "se3_exp_log_1M"
+    kernel = "batch_kernel_pf<SOA, OpSe3ExpLog> x8 (CUDA graph over 8 rotating 1M-twist buffer sets)"
+    n_default = 1 << 20
+    NBUF = 8
+
+    def setup(self):
+        self.bufs = []
+        for b in range(self.NBUF):
+            xi = _twists_soa(self.n, self.first + b * self.n, self.device)
+            self.bufs.append((xi, torch.empty_like(xi)))
+        self.xi = self.bufs[0][0]
+        for xi, out in self.bufs:  # warm-up outside the capture: occupancy queries, attribute calls
+            mb.se3_exp_log(xi, layout=mb.SOA, out=out)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            for xi, out in self.bufs:
+                mb.se3_exp_log(xi, layout=mb.SOA, out=out)
+        self.launches_per_step = self.NBUF
+        self.instances_per_step = self.NBUF * self.n
+
+    def step(self):
+        self.graph.replay()
+
+    def free_outputs(self):
+        self.graph = None
+        self.bufs = [(xi, None) for xi, _ in self.bufs]
 
 
 class LinsolveQR43(Workload):
@@ -118,6 +227,8 @@ class LinsolveQR43(Workload):
     kernel = "batch_kernel<SOA, OpLinsolveQR<4, 3>>"
     n_default = 1 << 26
     bytes_in, bytes_out = 96 + 32, 24 + 1
+    host_api = "ppx_cuda_host_linsolve_qr"
+    host_out = ((3, np.float64), (1, np.int8))
 
     def setup(self):
         r = _device_records(self.n, 16, synth.SEEDS[self.name], self.first, -1.0, 1.0, self.device)
@@ -129,12 +240,18 @@ class LinsolveQR43(Workload):
         self._keep = soa
 
     def step(self):
-        import ctypes as C
-        from ._lib import check, lib
-        check(lib.ppx_cuda_batch_linsolve_qr(4, 3, C.c_void_p(self.A.data_ptr()), C.c_void_p(self.b.data_ptr()),
-                                             C.c_void_p(self.x.data_ptr()), C.c_void_p(self.status.data_ptr()),
-                                             self.n, mb.SOA, self.n, mb._stream()))
+        check(lib.ppx_cuda_batch_linsolve_qr(4, 3, _vp(self.A), _vp(self.b), _vp(self.x), _vp(self.status), self.n,
+                                             mb.SOA, self.n, mb._stream()))
 
+    def free_outputs(self):
+        self.x = self.status = None
+
+    def host_inputs(self):
+        r = mb.to_aos(self._keep)
+        return [r[:, :12].contiguous(), r[:, 12:].contiguous()]
+
+    def host_call(self, n, ins, outs):
+        check(lib.ppx_cuda_host_linsolve_qr(4, 3, _hp(ins[0]), _hp(ins[1]), _hp(outs[0]), _hp(outs[1]), n))
 
 
 class Svd66(Workload):
@@ -144,6 +261,8 @@ class Svd66(Workload):
     n_default = 1 << 24
     bytes_in, bytes_out = 288, 288 + 48 + 288
     bound = "fp64"
+    host_api = "ppx_cuda_host_svd"
+    host_out = ((36, np.float64), (6, np.float64), (36, np.float64))
 
     def setup(self):
         r = _device_records(self.n, 36, synth.SEEDS[self.name], self.first, -1.0, 1.0, self.device)
@@ -154,12 +273,17 @@ class Svd66(Workload):
         self.w = torch.empty((6, self.n), dtype=torch.float64, device=self.device)
 
     def step(self):
-        import ctypes as C
-        from ._lib import check, lib
-        check(lib.ppx_cuda_batch_svd(6, 6, C.c_void_p(self.A.data_ptr()), C.c_void_p(self.U.data_ptr()),
-                                     C.c_void_p(self.w.data_ptr()), C.c_void_p(self.V.data_ptr()), self.n, mb.SOA,
-                                     self.n, mb._stream()))
+        check(lib.ppx_cuda_batch_svd(6, 6, _vp(self.A), _vp(self.U), _vp(self.w), _vp(self.V), self.n, mb.SOA, self.n,
+                                     mb._stream()))
 
+    def free_outputs(self):
+        self.U = self.V = self.w = None
+
+    def host_inputs(self):
+        return [mb.to_aos(self.A)]
+
+    def host_call(self, n, ins, outs):
+        check(lib.ppx_cuda_host_svd(6, 6, _hp(ins[0]), _hp(outs[0]), _hp(outs[1]), _hp(outs[2]), n))
 
 
 class EigSym4(Workload):
@@ -169,6 +293,8 @@ class EigSym4(Workload):
     n_default = 1 << 24
     bytes_in, bytes_out = 128, 32 + 128
     bound = "fp64"
+    host_api = "ppx_cuda_host_eig_sym"
+    host_out = ((4, np.float64), (16, np.float64))
 
     def setup(self):
         r = _device_records(self.n, 16, synth.SEEDS[self.name], self.first, -1.0, 1.0, self.device)
@@ -181,11 +307,17 @@ class EigSym4(Workload):
         self.z = torch.empty_like(self.S)
 
     def step(self):
-        import ctypes as C
-        from ._lib import check, lib
-        check(lib.ppx_cuda_batch_eig_sym(4, C.c_void_p(self.S.data_ptr()), C.c_void_p(self.d.data_ptr()),
-                                         C.c_void_p(self.z.data_ptr()), 1, self.n, mb.SOA, self.n, mb._stream()))
+        check(lib.ppx_cuda_batch_eig_sym(4, _vp(self.S), _vp(self.d), _vp(self.z), 1, self.n, mb.SOA, self.n,
+                                         mb._stream()))
 
+    def free_outputs(self):
+        self.d = self.z = None
+
+    def host_inputs(self):
+        return [mb.to_aos(self.S)]
+
+    def host_call(self, n, ins, outs):
+        check(lib.ppx_cuda_host_eig_sym(4, _hp(ins[0]), _hp(outs[0]), _hp(outs[1]), 1, n))
 
 
 class IkNewtonStep(Workload):
@@ -195,10 +327,13 @@ class IkNewtonStep(Workload):
     n_default = 1 << 25  # 256M over 8 GPUs
     bytes_in, bytes_out = 48 + 128, 48
     bound = "fp64"
+    host_api = "ppx_cuda_host_ik_newton_step"
+    host_out = ((6, np.float64),)
+    allow_lu = True
 
     def setup(self):
         self.kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
-        seed = synth.SEEDS[getattr(self, "seed_name", self.name)]
+        seed = synth.SEEDS["ik_newton_step"]
         q = _device_records(self.n, 6, seed, self.first, -np.pi, np.pi, self.device)
         d = _device_records(self.n, 6, seed ^ 0xA5A5, self.first, -0.05, 0.05, self.device)
         self.q = mb.to_soa(q)
@@ -208,24 +343,39 @@ class IkNewtonStep(Workload):
         del qd
         self.qo = torch.empty_like(self.q)
 
+    def _mode(self):
+        from . import _lib
+        return _lib.set_square_solve_lu(self.allow_lu)
+
     def step(self):
-        self.kin.ik_newton_step(self.q, self.Tt, layout=mb.SOA, out=self.qo)
+        from . import _lib
+        prev = self._mode()
+        try:
+            self.kin.ik_newton_step(self.q, self.Tt, layout=mb.SOA, out=self.qo)
+        finally:
+            _lib.set_square_solve_lu(prev)
+
+    def free_outputs(self):
+        self.qo = None
+
+    def host_inputs(self):
+        return [mb.to_aos(self.q), mb.to_aos(self.Tt)]
+
+    def host_call(self, n, ins, outs):
+        from . import _lib
+        prev = self._mode()
+        try:
+            check(lib.ppx_cuda_host_ik_newton_step(_hp(self.kin.screws), _hp(self.kin.home), 6, _hp(ins[0]), _hp(ins[1]),
+                                                   _hp(outs[0]), None, n))
+        finally:
+            _lib.set_square_solve_lu(prev)
 
 
 class IkNewtonStepSvd(IkNewtonStep):
     """config 5 with the pseudo-inverse solve forced through the Jacobi SVD on every instance (the fp64-bound variant)"""
     name = "ik_newton_step_svd"
     kernel = "batch_kernel_pf<SOA, OpIkStep<6>> (allow_lu = false)"
-    seed_name = "ik_newton_step"
-
-    def step(self):
-        from . import _lib
-        prev = _lib.set_square_solve_lu(False)
-        try:
-            self.kin.ik_newton_step(self.q, self.Tt, layout=mb.SOA, out=self.qo)
-        finally:
-            _lib.set_square_solve_lu(prev)
-
+    allow_lu = False
 
 
 class IkCodo(Workload):
@@ -234,9 +384,11 @@ class IkCodo(Workload):
     name = "inverse_space_codo"
     kernel = "ik_codo_kernel<AOS>"
     layout = "aos"
-    n_default = 1 << 24  # as config 2; the ~0.3 % of targets on which CoDo stalls for ITMAX = 300 trips leave a ~10 ms tail per launch
+    n_default = 1 << 24  # as config 2; the ~0.3 % of targets on which CoDo stalls for ITMAX = 300 trips leave a tail per launch
     bytes_in, bytes_out = 48 + 128, 48 + 8 + 1
     bound = "fp64 / latency (data-dependent iteration counts)"
+    host_api = "ppx_cuda_host_ik_codo"
+    host_out = ((6, np.float64), (1, np.float64), (1, np.int8))
 
     def setup(self):
         self.kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
@@ -248,5 +400,16 @@ class IkCodo(Workload):
     def step(self):
         self.out = self.kin.inverseSpace(self.Tt, self.q0, self.lo, self.hi)
 
+    def free_outputs(self):
+        self.out = None
 
-WORKLOADS = {w.name: w for w in (Ur5FkJacobian, Ur5FkJacobianAoS, Se3ExpLog, LinsolveQR43, Svd66, EigSym4, IkNewtonStep, IkNewtonStepSvd, IkCodo)}
+    def host_inputs(self):
+        return [self.Tt, self.q0]
+
+    def host_call(self, n, ins, outs):
+        check(lib.ppx_cuda_host_ik_codo(_hp(self.kin.screws), _hp(self.kin.home), 6, _hp(self.lo), _hp(self.hi),
+                                        _hp(ins[0]), _hp(ins[1]), _hp(outs[0]), None, _hp(outs[1]), _hp(outs[2]), n))
+
+
+WORKLOADS = {w.name: w for w in (Ur5FkJacobian, Ur5FkJacobianAoS, Se3ExpLog1M, Se3ExpLog, LinsolveQR43, Svd66, EigSym4,
+                                 IkNewtonStep, IkNewtonStepSvd, IkCodo)}

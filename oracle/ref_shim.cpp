@@ -63,10 +63,12 @@ namespace
                     size_t count, int nthreads)
     {
         const kinematics<N> chain = make_chain<N>(screws, home);
-#pragma omp parallel for schedule(static) num_threads(threads_or_all(nthreads))
+#pragma omp parallel num_threads(threads_or_all(nthreads))
+        {
+        kinematics<N> kin = chain; // one private copy per thread (jacobiSpace is non-const in the reference)
+#pragma omp for schedule(static)
         for (long long i = 0; i < (long long)count; i++)
         {
-            kinematics<N> kin = chain; // jacobiSpace is non-const in the reference
             const auto qi = load<N, 1>(q + N * i);
             if (T)
             {
@@ -77,6 +79,7 @@ namespace
                 store(Js + 6 * N * i, kin.jacobiSpace(qi)); // demo/robotics.hpp:94-106
             }
         }
+        }
         return 0;
     }
 
@@ -85,10 +88,12 @@ namespace
                 double *Vs_out, size_t count, int nthreads)
     {
         const kinematics<N> chain = make_chain<N>(screws, home);
-#pragma omp parallel for schedule(static) num_threads(threads_or_all(nthreads))
+#pragma omp parallel num_threads(threads_or_all(nthreads))
+        {
+        kinematics<N> kin = chain; // one private copy per thread
+#pragma omp for schedule(static)
         for (long long i = 0; i < (long long)count; i++)
         {
-            kinematics<N> kin = chain;
             auto qi = load<N, 1>(q + N * i);
             const SE3 pose(load<4, 4>(Tt + 16 * i));
             // test/lie_test.cpp:104-110
@@ -100,6 +105,7 @@ namespace
             {
                 store(Vs_out + 6 * i, Vs);
             }
+        }
         }
         return 0;
     }
