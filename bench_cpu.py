@@ -161,6 +161,13 @@ def cpu_op(name, oracle, n):
         out = np.empty((n, 9))
         _touch(out)
         return lambda: _ok(oracle.lib.ppxo_so3_jac(C.c_int(1), _d(w), _d(out), C.c_size_t(n), C.c_int(NTHREADS)))
+    if name.startswith("matmul_"):
+        m, k, l = (int(x) for x in name[len("matmul_"):].split("x"))
+        A, B = synth.dense(n, m, k, seed=0x301), synth.dense(n, k, l, seed=0x302)
+        out = np.empty((n, m * l))
+        _touch(out)
+        return lambda: _ok(oracle.lib.ppxo_matmul(C.c_int(m), C.c_int(k), C.c_int(l), _d(A), _d(B), _d(out), C.c_size_t(n),
+                                                  C.c_int(NTHREADS)))
     if name == "ik_solve_newton_loop":
         q = synth.joint_angles(n, seed=synth.SEEDS["ik_newton_step"])
         Tt = oracle.poe_fk_jacobian(S, M, q + synth.ik_offsets(n), want_Js=False)[0]

@@ -203,6 +203,13 @@ int ppx_cuda_host_get_devices(int *devices, int capacity);
 /* measurement helper: all configured devices copy at once through `host` (bytes, pinned) for `seconds`;
  * direction 0 H2D, 1 D2H, 2 both.  gbs[i] = GB/s device i sustained meanwhile: the ceiling of any host-buffer path. */
 int ppx_cuda_host_copy_probe(void *host, size_t bytes, int direction, double seconds, double *gbs);
+/* Chooses, among `candidates` (count ordinals; NULL / 0: every visible device), the devices whose host links carry the
+ * most when used together -- on multi-socket hosts the links interfere, and fewer devices can move more -- by greedy
+ * selection on measured copy rates (`seconds` per probe, 0.1-0.2 is plenty; direction as in the copy probe: choose the
+ * one that dominates the calls to come), and makes them the device list.  `host` (bytes, pinned) is scratch for the
+ * copies.  *aggregate_gbs (may be NULL) = what the chosen set sustains.  Read the choice with ppx_cuda_host_get_devices. */
+int ppx_cuda_host_tune_devices(const int *candidates, int count, void *host, size_t bytes, int direction, double seconds,
+                               double *aggregate_gbs);
 int ppx_cuda_host_matmul(int m, int n, int l, const double *A, const double *B, double *C, size_t count);
 int ppx_cuda_host_so3_exp(const double *w, double *R, size_t n);
 int ppx_cuda_host_SO3_log(const double *R, double *w, size_t n);

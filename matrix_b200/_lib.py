@@ -94,6 +94,7 @@ _SIGNATURES = {
     "ppx_cuda_host_set_devices": [C.POINTER(C.c_int), _i],
     "ppx_cuda_host_get_devices": [C.POINTER(C.c_int), _i],
     "ppx_cuda_host_copy_probe": [_vp, _sz, _i, _d, C.POINTER(_d)],
+    "ppx_cuda_host_tune_devices": [C.POINTER(C.c_int), _i, _vp, _sz, _i, _d, C.POINTER(_d)],
 }
 _RESTYPES = {
     "ppx_cuda_version": (C.c_char_p, []),

@@ -338,72 +338,13 @@ int pipeline(const std::vector<HostIn> &ins, const std::vector<HostOut> &outs, s
     return job.rc.load();
 }
 
-constexpr size_t D = sizeof(double);
-typedef const double *cd;
-typedef double *md;
-
-} // namespace
-
-extern "C"
+// the copy loop behind ppx_cuda_host_copy_probe / ppx_cuda_host_tune_devices: all `devs` copy at once
+int probe_devices(const std::vector<int> &devs, void *host, size_t bytes, int direction, double seconds, double *gbs)
 {
-
-int ppx_cuda_host_trim(void) { return ppx_scratch_trim(); }
-
-int ppx_cuda_host_set_devices(const int *devices, int count)
-{
-    std::vector<int> v;
-    if (count < 0) // all visible devices
-    {
-        int have = 0;
-        if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1)
-            return PPX_ERR_NO_DEVICE;
-        for (int d = 0; d < have && d < MAX_DEVICES; d++)
-            v.push_back(d);
-    }
-    else if (count > 0)
-    {
-        if (!devices || count > MAX_DEVICES)
-            return PPX_ERR_BAD_ARGUMENT;
-        int have = 0;
-        if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1)
-            return PPX_ERR_NO_DEVICE;
-        for (int i = 0; i < count; i++)
-        {
-            if (devices[i] < 0 || devices[i] >= have || std::find(v.begin(), v.end(), devices[i]) != v.end())
-                return PPX_ERR_BAD_ARGUMENT;
-            v.push_back(devices[i]);
-        }
-    }
-    std::lock_guard<std::mutex> lock(g_dev_mu);
-    g_devices.swap(v);
-    g_devices_set = true;
-    return PPX_OK;
-}
-
-int ppx_cuda_host_get_devices(int *devices, int capacity)
-{
-    const std::vector<int> v = host_devices();
-    for (int i = 0; i < (int)v.size() && i < capacity && devices; i++)
-        devices[i] = v[i];
-    return (int)v.size();
-}
-
-// Measurement helper: what the host-device links of the configured devices carry when all of them copy at once.
-// `host` is cut into one contiguous slice per device; every worker copies through its slice in chunks of the
-// pipeline's size (device scratch of two chunks, two streams) again and again until `seconds` have passed, all
-// workers starting together.  direction: 0 H2D, 1 D2H, 2 both at once (one stream each, on the two halves of the
-// slice).  gbs[i] = bytes device i moved / elapsed.  No kernel runs: this is the ceiling of any host-buffer path.
-int ppx_cuda_host_copy_probe(void *host, size_t bytes, int direction, double seconds, double *gbs)
-{
-    if (!host || !gbs || bytes == 0 || direction < 0 || direction > 2 || !(seconds > 0.0))
-        return PPX_ERR_BAD_ARGUMENT;
-    std::vector<int> devs = host_devices();
     int home = -1;
     cudaError_t e = cudaGetDevice(&home);
     if (e != cudaSuccess)
         return (int)e;
-    if (devs.empty())
-        devs.push_back(home);
     const size_t G = devs.size();
     const size_t slice = bytes / G / 4096 * 4096;
     const size_t piece = std::min(env_chunk_bytes(), slice / 2 / 4096 * 4096);
@@ -475,6 +416,168 @@ int ppx_cuda_host_copy_probe(void *host, size_t bytes, int direction, double sec
         t.join();
     cudaSetDevice(home);
     return rc.load();
+}
+
+constexpr size_t D = sizeof(double);
+typedef const double *cd;
+typedef double *md;
+
+} // namespace
+
+extern "C"
+{
+
+int ppx_cuda_host_trim(void) { return ppx_scratch_trim(); }
+
+int ppx_cuda_host_set_devices(const int *devices, int count)
+{
+    std::vector<int> v;
+    if (count < 0) // all visible devices
+    {
+        int have = 0;
+        if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1)
+            return PPX_ERR_NO_DEVICE;
+        for (int d = 0; d < have && d < MAX_DEVICES; d++)
+            v.push_back(d);
+    }
+    else if (count > 0)
+    {
+        if (!devices || count > MAX_DEVICES)
+            return PPX_ERR_BAD_ARGUMENT;
+        int have = 0;
+        if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1)
+            return PPX_ERR_NO_DEVICE;
+        for (int i = 0; i < count; i++)
+        {
+            if (devices[i] < 0 || devices[i] >= have || std::find(v.begin(), v.end(), devices[i]) != v.end())
+                return PPX_ERR_BAD_ARGUMENT;
+            v.push_back(devices[i]);
+        }
+    }
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    g_devices.swap(v);
+    g_devices_set = true;
+    return PPX_OK;
+}
+
+int ppx_cuda_host_get_devices(int *devices, int capacity)
+{
+    const std::vector<int> v = host_devices();
+    for (int i = 0; i < (int)v.size() && i < capacity && devices; i++)
+        devices[i] = v[i];
+    return (int)v.size();
+}
+
+// Measurement helper: what the host-device links of the configured devices carry when all of them copy at once.
+// `host` is cut into one contiguous slice per device; every worker copies through its slice in chunks of the
+// pipeline's size (device scratch of two chunks, two streams) again and again until `seconds` have passed, all
+// workers starting together.  direction: 0 H2D, 1 D2H, 2 both at once (one stream each, on the two halves of the
+// slice).  gbs[i] = bytes device i moved / elapsed.  No kernel runs: this is the ceiling of any host-buffer path.
+int ppx_cuda_host_copy_probe(void *host, size_t bytes, int direction, double seconds, double *gbs)
+{
+    if (!host || !gbs || bytes == 0 || direction < 0 || direction > 2 || !(seconds > 0.0))
+        return PPX_ERR_BAD_ARGUMENT;
+    std::vector<int> devs = host_devices();
+    if (devs.empty())
+    {
+        int cur = 0;
+        const cudaError_t e = cudaGetDevice(&cur);
+        if (e != cudaSuccess)
+            return (int)e;
+        devs.push_back(cur);
+    }
+    return probe_devices(devs, host, bytes, direction, seconds, gbs);
+}
+
+// Picks, among `candidates`, the devices whose host links carry the most WHEN USED TOGETHER and makes them the device
+// list of the host face.  On a multi-socket host the links are not independent: on the 8 x B200 box this was developed
+// on, devices 0-3 reach host memory through a path that gives the four of them 40 GB/s of D2H in total and, while they
+// use it, halves what devices 4-7 get (all eight together: 90 GB/s; devices 4-7 alone: 175 GB/s) -- so for a
+// D2H-bound call four devices are faster than eight.  Greedy selection on measured rates (ppx_cuda_host_copy_probe's
+// loop, `seconds` per probe): every candidate alone; then, starting from the fastest, the candidate whose addition
+// raises the aggregate most is added -- taken at once, without trying the others, if it keeps at least half of its
+// solo rate -- until no addition gains 3 %.  ~20 probes for 8 devices.  *aggregate_gbs = rate of the chosen set.
+int ppx_cuda_host_tune_devices(const int *candidates, int count, void *host, size_t bytes, int direction, double seconds,
+                               double *aggregate_gbs)
+{
+    if (!host || bytes == 0 || direction < 0 || direction > 2 || !(seconds > 0.0) || count > MAX_DEVICES)
+        return PPX_ERR_BAD_ARGUMENT;
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1)
+        return PPX_ERR_NO_DEVICE;
+    std::vector<int> cand;
+    if (candidates && count > 0)
+    {
+        for (int i = 0; i < count; i++)
+        {
+            if (candidates[i] < 0 || candidates[i] >= have ||
+                std::find(cand.begin(), cand.end(), candidates[i]) != cand.end())
+                return PPX_ERR_BAD_ARGUMENT;
+            cand.push_back(candidates[i]);
+        }
+    }
+    else
+        for (int d = 0; d < have && d < MAX_DEVICES; d++)
+            cand.push_back(d);
+    auto rate = [&](const std::vector<int> &set, double &agg) {
+        std::vector<double> g(set.size(), 0.0);
+        const int rc = probe_devices(set, host, bytes, direction, seconds, g.data());
+        agg = 0.0;
+        for (double x : g)
+            agg += x;
+        return rc;
+    };
+    std::vector<double> solo(cand.size(), 0.0);
+    for (size_t i = 0; i < cand.size(); i++)
+    {
+        const int rc = rate({cand[i]}, solo[i]);
+        if (rc != PPX_OK)
+            return rc;
+    }
+    std::vector<size_t> order(cand.size());
+    for (size_t i = 0; i < order.size(); i++)
+        order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return solo[x] > solo[y]; });
+    std::vector<int> chosen{cand[order[0]]};
+    std::vector<bool> used(cand.size(), false);
+    used[order[0]] = true;
+    double best = solo[order[0]];
+    for (;;)
+    {
+        size_t pick = cand.size();
+        double pick_rate = best;
+        for (size_t oi = 0; oi < order.size(); oi++)
+        {
+            const size_t i = order[oi];
+            if (used[i])
+                continue;
+            std::vector<int> trial = chosen;
+            trial.push_back(cand[i]);
+            double agg = 0.0;
+            const int rc = rate(trial, agg);
+            if (rc != PPX_OK)
+                return rc;
+            if (agg > pick_rate)
+            {
+                pick = i;
+                pick_rate = agg;
+            }
+            if (agg - best >= 0.5 * solo[i])
+                break; // this link is (nearly) independent of the chosen ones: take it
+        }
+        if (pick == cand.size() || pick_rate < 1.03 * best)
+            break;
+        used[pick] = true;
+        chosen.push_back(cand[pick]);
+        best = pick_rate;
+    }
+    std::sort(chosen.begin(), chosen.end());
+    if (aggregate_gbs)
+        *aggregate_gbs = best;
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    g_devices = chosen;
+    g_devices_set = true;
+    return PPX_OK;
 }
 
 int ppx_cuda_host_matmul(int m, int n, int l, const double *A, const double *B, double *C, size_t count)

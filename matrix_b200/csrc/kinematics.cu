@@ -39,8 +39,10 @@ namespace
 template <int NJ, bool WANT_T, bool WANT_J>
 struct OpFkJacobian
 {
+    // 3 CTAs of 128 per SM (168 registers): the record (AoS) layout then needs no spills around its staging tile and
+    // reaches 0.94 of the HBM peak (0.86 at 4 CTAs / 128 registers); the component-plane layout is indifferent (0.905)
 #ifndef PPX_FK_MINB
-#define PPX_FK_MINB 4
+#define PPX_FK_MINB 3
 #endif
     static constexpr int BLOCK = 128, MINB = PPX_FK_MINB, MAXW = (WANT_J ? 6 * NJ : 16) > 16 ? (WANT_J ? 6 * NJ : 16) : 16;
     ChainConst<NJ> ch;
@@ -94,13 +96,12 @@ __device__ __forceinline__ typename std::enable_if<NJ != 6>::type svd_solve_disp
     jacobi_svd_solve<6, NJ>(js, V, w2, vs, dq);
 }
 
-// Vs = Ad(T(q)) log(T(q)^-1 Tt),  dq = pinv(Js(q)) Vs  (test/lie_test.cpp:104-110)
+// Js(q) and Vs = Ad(T(q)) log(T(q)^-1 Tt)  (test/lie_test.cpp:104-108)
 template <int NJ>
-__device__ __forceinline__ void ik_newton_update(const ChainConst<NJ> &ch, const Rigid &target, double (&q)[NJ],
-                                                 double (&vs)[6], bool allow_lu)
+__device__ __forceinline__ void ik_residual(const ChainConst<NJ> &ch, const Rigid &target, const double (&q)[NJ],
+                                            double (&js)[6 * NJ], double (&vs)[6])
 {
     Rigid t, ti, x;
-    double js[6 * NJ];
     poe_fk_jacobian<NJ, true, true>(ch, q, t, [&](int col, const double(&v)[6]) {
 #pragma unroll
         for (int k = 0; k < 6; k++)
@@ -112,6 +113,15 @@ __device__ __forceinline__ void ik_newton_update(const ChainConst<NJ> &ch, const
     SE3_log(x, lg);
     const double lw[3] = {lg[0], lg[1], lg[2]}, lv[3] = {lg[3], lg[4], lg[5]};
     rigid_adjoint_apply(t, lw, lv, vs);
+}
+
+// q <- q + pinv(Js(q)) Vs, the whole step in one thread (the Newton loop ik_solve_kernel uses this form)
+template <int NJ>
+__device__ __forceinline__ void ik_newton_update(const ChainConst<NJ> &ch, const Rigid &target, double (&q)[NJ],
+                                                 double (&vs)[6], bool allow_lu)
+{
+    double js[6 * NJ];
+    ik_residual<NJ>(ch, target, q, js, vs);
     double dq[NJ];
     svd_solve_dispatch<NJ>(js, vs, dq, allow_lu);
 #pragma unroll
@@ -119,27 +129,31 @@ __device__ __forceinline__ void ik_newton_update(const ChainConst<NJ> &ch, const
         q[i] += dq[i];
 }
 
-// BASELINE config 5.  48 + 128 B in, 48 B out; ~960 fp64 instructions on the LU path of the solve (the common case),
-// ~6300 when the Jacobi SVD fallback runs.
-// 3 CTAs per SM (168 registers): +4 % over 2 now that the common path is the LU solve; the Jacobi fallback spills 48 B
+// BASELINE config 5, 48 + 128 B in, 48 B out.  Two kernels for the 6-joint step (ik_step_n):
+//
+//   OpIkStepLU   the step with the square pseudo-inverse solve done by LU with partial pivoting -- valid whenever the
+//                rigorous condition bound read off the factors stays below 1e10 (square_pinv_solve's argument).  A lane
+//                whose system fails that test marks its instance in a byte map.  No Jacobi code in this kernel: the
+//                common path keeps its own register allocation and instruction footprint.
+//   OpIkStepSvd  the step with the Jacobi SVD solve (the reference's truncation).  With a byte map it is the second
+//                pass: a warp looks at its 32 marks and, if none is set, is done; otherwise it recomputes its 32
+//                instances and replaces the marked ones.  Without a map (ppx_cuda_set_square_solve_lu(0), or fewer
+//                than 6 joints, a genuine least-squares problem) it is the whole step.
 #ifndef PPX_IK_MINB
 #define PPX_IK_MINB 3
 #endif
-template <int NJ>
-struct OpIkStep
+struct OpIkStepLU
 {
+    static constexpr int NJ = 6;
     static constexpr int BLOCK = 128, MINB = PPX_IK_MINB, MAXW = 16;
     ChainConst<NJ> ch;
     const double *q;
     const double *Tt;
     double *q_out;
     double *Vs;
-    bool allow_lu;
-#ifndef PPX_IK_PREFETCH
-#define PPX_IK_PREFETCH 1
-#endif
+    unsigned char *hard; // one byte per instance, zeroed before the launch
     // joint angles and target pose of the next tile staged (cp.async) behind the arithmetic of the current one
-    static constexpr bool PREFETCH = PPX_IK_PREFETCH != 0;
+    static constexpr bool PREFETCH = true;
     static constexpr int IN_WIDTH = NJ + 16 + 2;
     template <class IO>
     __device__ __forceinline__ void prefetch(const IO &io, double *stage) const
@@ -150,29 +164,77 @@ struct OpIkStep
     template <class IO>
     __device__ __forceinline__ void compute_store(const IO &io, const double *stage) const
     {
-        double qi[NJ], m[16];
+        double qi[NJ], m[16], js[36], vs[6], dq[NJ];
         io.template read_staged<NJ>(stage, qi);
         io.template read_staged<16>(stage + IO::stage_doubles(BLOCK, NJ), m);
-        step_store(io, qi, m);
-    }
-    template <class IO>
-    __device__ __forceinline__ void operator()(const IO &io) const
-    {
-        double qi[NJ], m[16];
-        io.load(q, qi);
-        io.load(Tt, m);
-        step_store(io, qi, m);
-    }
-    template <class IO>
-    __device__ __forceinline__ void step_store(const IO &io, double (&qi)[NJ], const double (&m)[16]) const
-    {
-        double vs[6];
         Rigid target;
         rigid_from_record(m, target);
-        ik_newton_update<NJ>(ch, target, qi, vs, allow_lu);
+        ik_residual<NJ>(ch, target, qi, js, vs);
+#pragma unroll
+        for (int i = 0; i < NJ; i++)
+            dq[i] = vs[i];
+        bool even;
+        double ipiv[NJ];
+        lu_factor_solve<NJ, 1>(js, dq, even, ipiv);
+        const bool easy = lu_cond_bound<NJ>(js, ipiv) < SQUARE_LU_COND_MAX;
+        // a marked instance leaves this pass with its ORIGINAL q in q_out: the second pass then needs q_out alone,
+        // so the call stays correct when q_out aliases q (in-place update)
+#pragma unroll
+        for (int i = 0; i < NJ; i++)
+            qi[i] = easy ? qi[i] + dq[i] : qi[i];
         io.store(q_out, qi);
         if (Vs != nullptr)
             io.store(Vs, vs);
+        if (!easy && io.valid)
+            hard[io.i] = 1;
+    }
+};
+
+template <int NJ>
+struct OpIkStepSvd
+{
+    static constexpr int BLOCK = 128, MINB = 2, MAXW = 16;
+    ChainConst<NJ> ch;
+    const double *q;
+    const double *Tt;
+    double *q_out;
+    double *Vs;
+    const unsigned char *hard; // nullptr: every instance
+    template <class IO>
+    __device__ __forceinline__ void operator()(const IO &io) const
+    {
+        const bool mine = hard == nullptr || (io.valid && hard[io.i] != 0);
+        if (hard != nullptr && !__any_sync(0xffffffffu, mine))
+            return; // nothing marked among this warp's 32 instances
+        double qi[NJ], m[16], js[6 * NJ], vs[6], dq[NJ], prev[NJ], pvs[6];
+        // second pass: q_out holds the first pass's result -- the updated q of the unmarked lanes (kept), the original
+        // q of the marked ones (see OpIkStepLU); unmarked lanes run the arithmetic on whatever they hold (the Jacobi
+        // sweeps end by warp vote, every lane has to take part) and their values are dropped
+        io.load(hard != nullptr ? q_out : q, qi);
+        io.load(Tt, m);
+        if (hard != nullptr && Vs != nullptr)
+            io.load(Vs, pvs);
+#pragma unroll
+        for (int i = 0; i < NJ; i++)
+            prev[i] = qi[i];
+        Rigid target;
+        rigid_from_record(m, target);
+        ik_residual<NJ>(ch, target, qi, js, vs);
+        svd_solve_dispatch<NJ>(js, vs, dq, false);
+#pragma unroll
+        for (int i = 0; i < NJ; i++)
+            qi[i] = mine ? qi[i] + dq[i] : prev[i];
+        io.store(q_out, qi);
+        if (Vs != nullptr)
+        {
+            if (hard != nullptr)
+            {
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+                    vs[i] = mine ? vs[i] : pvs[i];
+            }
+            io.store(Vs, vs);
+        }
     }
 };
 
@@ -391,13 +453,46 @@ int fk_jacobian_n(const double *screws, const double *home, const double *q, dou
     return dispatch(layout, OpFkJacobian<NJ, false, true>{ch, q, nullptr, Js}, n, ld, stream);
 }
 
+// fewer than 6 joints: the Jacobi SVD step on every instance
 template <int NJ>
 int ik_step_n(const double *screws, const double *home, const double *q, const double *Tt, double *q_out,
               double *Vs, size_t n, int layout, size_t ld, void *stream)
 {
     ChainConst<NJ> ch;
     fold_chain<NJ>(screws, home, ch);
-    return dispatch(layout, OpIkStep<NJ>{ch, q, Tt, q_out, Vs, g_ppx_square_lu.load(std::memory_order_relaxed) != 0}, n, ld, stream);
+    return dispatch(layout, OpIkStepSvd<NJ>{ch, q, Tt, q_out, Vs, nullptr}, n, ld, stream);
+}
+
+// 6 joints: the LU pass over everything, then the SVD pass over what the LU pass marked (see OpIkStepLU).  The byte
+// map lives for this call only (stream-ordered allocation from the library's retained pool).
+int ik_step_6(const double *screws, const double *home, const double *q, const double *Tt, double *q_out, double *Vs,
+              size_t n, int layout, size_t ld, void *stream)
+{
+    ChainConst<6> ch;
+    fold_chain<6>(screws, home, ch);
+    if (g_ppx_square_lu.load(std::memory_order_relaxed) == 0)
+        return dispatch(layout, OpIkStepSvd<6>{ch, q, Tt, q_out, Vs, nullptr}, n, ld, stream);
+    if (layout != PPX_LAYOUT_AOS && layout != PPX_LAYOUT_SOA)
+        return PPX_ERR_BAD_LAYOUT;
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess)
+        return (int)e;
+    cudaMemPool_t pool = nullptr;
+    int rc = ppx_scratch_pool(device, &pool);
+    if (rc != PPX_OK)
+        return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char *hard = nullptr;
+    e = cudaMallocFromPoolAsync((void **)&hard, n, pool, s);
+    if (e != cudaSuccess)
+        return (int)e;
+    e = cudaMemsetAsync(hard, 0, n, s);
+    rc = e != cudaSuccess ? (int)e : dispatch(layout, OpIkStepLU{ch, q, Tt, q_out, Vs, hard}, n, ld, stream);
+    if (rc == PPX_OK)
+        rc = dispatch(layout, OpIkStepSvd<6>{ch, q, Tt, q_out, Vs, hard}, n, ld, stream);
+    const cudaError_t fe = cudaFreeAsync(hard, s);
+    return rc != PPX_OK ? rc : (int)fe;
 }
 
 // Launch of a persistent kernel with a work counter: as many CTAs as are resident at once; the counter lives for this
@@ -492,7 +587,7 @@ int ppx_cuda_batch_ik_newton_step(const double *screws, const double *home, int 
     case 3: return ik_step_n<3>(screws, home, q, Ttarget, q_out, Vs, n, layout, ld, stream);
     case 4: return ik_step_n<4>(screws, home, q, Ttarget, q_out, Vs, n, layout, ld, stream);
     case 5: return ik_step_n<5>(screws, home, q, Ttarget, q_out, Vs, n, layout, ld, stream);
-    case 6: return ik_step_n<6>(screws, home, q, Ttarget, q_out, Vs, n, layout, ld, stream);
+    case 6: return ik_step_6(screws, home, q, Ttarget, q_out, Vs, n, layout, ld, stream);
     }
     return PPX_ERR_BAD_SHAPE;
 }

@@ -355,7 +355,11 @@ PPX_DEV unsigned codo_trip_head(const double (&lo)[6], const double (&hi)[6], Co
             // on the bound itself (a legal start) the reference divides by zero: d = 1 / inf = 0 -> DIVERGED below
             const bool on_bound = (up || dn) && !(den >= 1e-290);
             const double bend = (up || dn) ? num * rcp_nr(den) : 0.0;
-            d[i] = on_bound ? 0.0 : rcp_nr(lambda + bend); // lambda >= 1e-2
+            // lambda >= 1e-2.  A denominator that overflowed (huge gradient next to a bound) gives the reference
+            // d = 1 / inf = 0 and the DIVERGED exit below; the branch-free reciprocal would return NaN there, which
+            // fmin() drops -- so a non-finite denominator is mapped to d = 0 explicitly (NaN inputs end the same way)
+            const double dd = lambda + bend;
+            d[i] = (on_bound || !(fabs(dd) <= DBL_MAX)) ? 0.0 : rcp_nr(dd);
         }
         if (codo_min6(d) < EPS_DP)
         {

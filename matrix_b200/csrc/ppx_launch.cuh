@@ -33,10 +33,23 @@ int ppx_scratch_trim();                                // util.cu: give the reta
 namespace ppx_dev
 {
 
+// An op may ask for a one-off start delay of the upper half of the CTA's warps (DESYNC_NS): kernels that alternate
+// between phases bound by different pipes then run the two warps that share a scheduler in opposite phases.
+template <class Op, class = void>
+struct desync_ns : std::integral_constant<int, 0>
+{
+};
+template <class Op>
+struct desync_ns<Op, typename std::enable_if<(Op::DESYNC_NS > 0)>::type> : std::integral_constant<int, Op::DESYNC_NS>
+{
+};
+
 template <int LAYOUT, class Op>
 __global__ void __launch_bounds__(Op::BLOCK, Op::MINB) batch_kernel(const __grid_constant__ Op op, size_t n, size_t ld)
 {
     extern __shared__ __align__(16) double ppx_smem[];
+    if (desync_ns<Op>::value > 0 && (threadIdx.x >> 5) >= Op::BLOCK / 64)
+        __nanosleep(desync_ns<Op>::value);
     const size_t stride = (size_t)gridDim.x * Op::BLOCK;
     for (size_t base = (size_t)blockIdx.x * Op::BLOCK; base < n; base += stride)
     {

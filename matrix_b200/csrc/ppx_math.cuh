@@ -11,6 +11,7 @@
 
 #include <cfloat>
 #include <cmath>
+#include <cstring>
 
 namespace ppx_dev
 {
@@ -26,13 +27,25 @@ constexpr double PI = 3.141592653589793;          // include/exprtmpl.hpp:11
 // sqrt() and operator/ there is no special-case slow path, hence no call and no convergence barrier in the
 // instruction stream: the independent rotation chains of a Jacobi round stay in one basic block and overlap.
 // (x = 0 gives inf/NaN; callers discard that lane's result with a select.)
+#ifndef __CUDA_ARCH__
+// host build of the device math (tests/cpp): a seed of the hardware's quality -- the exact value with its mantissa cut
+// to 23 bits -- over the whole fp64 exponent range (a cast to float would overflow below 1e-77)
+inline double ppx_host_seed(double y)
+{
+    unsigned long long u;
+    memcpy(&u, &y, 8);
+    u &= 0xFFFFFFFFE0000000ull;
+    memcpy(&y, &u, 8);
+    return y;
+}
+#endif
 PPX_DEV double rsqrt_nr(double x)
 {
     double y;
 #ifdef __CUDA_ARCH__
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
 #else
-    y = (double)(float)(1.0 / sqrt(x)); // host build of the device math (tests/cpp/codo_host.cpp): a seed of the same quality
+    y = ppx_host_seed(1.0 / sqrt(x));
 #endif
     const double e = fma(-(x * y), y, 1.0); // 1 - x y^2
     return fma(y * e, fma(0.375, e, 0.5), y); // y (1 + e/2 + 3 e^2/8)
@@ -43,11 +56,38 @@ PPX_DEV double rcp_nr(double x)
 #ifdef __CUDA_ARCH__
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
 #else
-    y = (double)(float)(1.0 / x);
+    y = ppx_host_seed(1.0 / x);
 #endif
     const double e = fma(-x, y, 1.0); // 1 - x y
     return fma(y, fma(e, e, e), y);   // y (1 + e + e^2)
 }
+
+// fp32 counterparts for the single-precision preconditioning sweeps of the Jacobi SVD (full fp32 accuracy is plenty:
+// that phase only has to find an approximately diagonalising basis)
+PPX_DEV float rsqrt_nr(float x)
+{
+#ifdef __CUDA_ARCH__
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); // one MUFU, 2 ulp
+    return y;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+PPX_DEV float rcp_nr(float x)
+{
+#ifdef __CUDA_ARCH__
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); // one MUFU, 1 ulp
+    return y;
+#else
+    return 1.0f / x;
+#endif
+}
+PPX_DEV float t_fma(float a, float b, float c) { return fmaf(a, b, c); }
+PPX_DEV double t_fma(double a, double b, double c) { return fma(a, b, c); }
+PPX_DEV float t_abs(float a) { return fabsf(a); }
+PPX_DEV double t_abs(double a) { return fabs(a); }
 
 // Rigid transform: rotation r (column-major, r[i + 3 j]) and translation p.  An SE3 record is
 // [r0 r1 r2 0 | r3 r4 r5 0 | r6 r7 r8 0 | p0 p1 p2 1] (include/liegroup.hpp:186-200).
@@ -388,6 +428,8 @@ struct JointConst
     double iw;      // 1/|omega|       (0 when omega = 0)
     double iw2;     // 1/|omega|^2     (0 when omega = 0)
     double iw3;     // 1/|omega|^3     (0 when omega = 0)
+    double sgn;     // kind != 0: omega = sgn * e_(kind-1), sgn = +-1
+    int kind;       // 0: general screw; 1, 2, 3: revolute about the x, y, z axis of the space frame (unit omega)
 };
 
 template <int NJ>
@@ -421,6 +463,16 @@ inline void fold_chain(const double *screws, const double *home, ChainConst<NJ> 
         j.iw = j.wn > 0.0 ? 1.0 / j.wn : 0.0;
         j.iw2 = j.iw * j.iw;
         j.iw3 = j.iw2 * j.iw;
+        // a unit rotation axis along a coordinate axis (the joints of every industrial arm in its home pose, all six of
+        // the UR5's): the kernels then use the structure of that rotation instead of a dense 3x3 (poe_joint)
+        j.kind = 0;
+        j.sgn = 1.0;
+        for (int a = 0; a < 3; a++)
+            if (fabs(j.w[a]) == 1.0 && j.w[(a + 1) % 3] == 0.0 && j.w[(a + 2) % 3] == 0.0)
+            {
+                j.kind = a + 1;
+                j.sgn = j.w[a];
+            }
     }
     for (int c = 0; c < 3; c++)
         for (int r = 0; r < 3; r++)
@@ -458,37 +510,131 @@ PPX_DEV void screw_exp(const JointConst &j, double q, Rigid &t)
         t.p[i] = fma(e, j.wwv[i], fma(b, j.wv[i], q * j.v[i]));
 }
 
+// One joint of the product-of-exponentials chain: emits column i of the space Jacobian, Ad(P) S_i, from the prefix
+// product P = e^{S_0 q_0} ... e^{S_{i-1} q_{i-1}} and then advances P <- P e^{S_i q_i}.
+//
+// KIND = 0: any screw (screw_exp + dense rigid product, ~98 fp64 instructions per joint).
+// KIND = A + 1: omega = sgn e_A, a unit axis of the space frame.  exp(S q) then rotates by sgn*q ABOUT e_A, i.e. it
+// leaves column A of P.R alone and mixes the other two with (cos, sin): 12 instructions instead of the dense 27, its
+// rotation matrix is never formed, and R omega is sgn * column A -- ~54 instructions per joint.  Same formulas as the
+// general path with the zeros and ones of omega taken out, so the results agree to the last bits (association of the
+// sums differs) and the |x| < EPS_SP identity branch of se3::exp (liegroup.hpp:258-261) is the same select.
+template <int KIND, class Emit>
+PPX_DEV void poe_joint(const JointConst &j, double q, Rigid &P, int i, bool first, bool want_col, bool advance, Emit &&emit)
+{
+    if (KIND == 0)
+    {
+        if (want_col)
+        {
+            double col[6];
+            if (first)
+            {
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    col[k] = j.w[k], col[3 + k] = j.v[k];
+            }
+            else
+                rigid_adjoint_apply(P, j.w, j.v, col);
+            emit(i, col);
+        }
+        if (advance)
+        {
+            if (first)
+                screw_exp(j, q, P);
+            else
+            {
+                Rigid E, Q;
+                screw_exp(j, q, E);
+                rigid_mul(P, E, Q);
+                P = Q;
+            }
+        }
+        return;
+    }
+    constexpr int A = KIND > 0 ? KIND - 1 : 0, B = (A + 1) % 3, C = (A + 2) % 3;
+    if (want_col)
+    {
+        double col[6];
+        if (first)
+        {
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                col[k] = j.w[k], col[3 + k] = j.v[k];
+        }
+        else
+        {
+            // (R w ; p x (R w) + R v) with R w = sgn * column A of R
+            const double rw[3] = {j.sgn * P.r[3 * A], j.sgn * P.r[3 * A + 1], j.sgn * P.r[3 * A + 2]};
+            double rv[3], c[3];
+            rot_apply(P.r, j.v, rv);
+            cross3(P.p, rw, c);
+            col[0] = rw[0], col[1] = rw[1], col[2] = rw[2];
+            col[3] = c[0] + rv[0], col[4] = c[1] + rv[1], col[5] = c[2] + rv[2];
+        }
+        emit(i, col);
+    }
+    if (advance)
+    {
+        double s, c;
+        sincos(q, &s, &c); // |omega| = 1: x = q
+        const bool tiny = fabs(q) < EPS_SP;
+        const double sn = tiny ? 0.0 : j.sgn * s; // rotation about +e_A by sgn*q
+        const double cs = tiny ? 1.0 : c;
+        const double b = tiny ? 0.0 : 1.0 - c;
+        const double e = tiny ? 0.0 : q - s;
+        double ep[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            ep[k] = fma(e, j.wwv[k], fma(b, j.wv[k], q * j.v[k]));
+        if (first)
+        {
+#pragma unroll
+            for (int k = 0; k < 9; k++)
+                P.r[k] = 0.0;
+            P.r[A + 3 * A] = 1.0;
+            P.r[B + 3 * B] = cs, P.r[C + 3 * B] = sn;   // column B = c e_B + s e_C
+            P.r[B + 3 * C] = -sn, P.r[C + 3 * C] = cs;  // column C = -s e_B + c e_C
+            P.p[0] = ep[0], P.p[1] = ep[1], P.p[2] = ep[2];
+        }
+        else
+        {
+            double np[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                np[k] = fma(P.r[k + 6], ep[2], fma(P.r[k + 3], ep[1], fma(P.r[k], ep[0], P.p[k])));
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+            {
+                const double xb = P.r[k + 3 * B], xc = P.r[k + 3 * C];
+                P.r[k + 3 * B] = fma(sn, xc, cs * xb);
+                P.r[k + 3 * C] = fma(cs, xc, -sn * xb);
+                P.p[k] = np[k];
+            }
+        }
+    }
+}
+
 // forwardSpace + jacobiSpace in one pass (demo/robotics.hpp:83-106).  The prefix products
 // P_i = e^{S_0 q_0} ... e^{S_{i-1} q_{i-1}} are shared: column i of Js is Ad(P_i) S_i and the pose is
 // P_N M.  (The reference associates forwardSpace right-to-left; sharing the prefixes changes the
 // association, a 1e-16 effect.)  Each Jacobian column is handed to `emit(i, col)` as soon as it exists,
-// so a caller that streams columns out never holds the 6 x NJ matrix in registers.
+// so a caller that streams columns out never holds the 6 x NJ matrix in registers.  The kind of every joint is a
+// per-call constant (constant bank), so the switch below is a uniform branch: no divergence, and only the variant a
+// chain uses is ever fetched.
 template <int NJ, bool WANT_T, bool WANT_J, class Emit>
 PPX_DEV void poe_fk_jacobian(const ChainConst<NJ> &ch, const double (&q)[NJ], Rigid &T, Emit &&emit)
 {
     Rigid P;
-    if (WANT_J)
-    {
-        const double col[6] = {ch.joint[0].w[0], ch.joint[0].w[1], ch.joint[0].w[2],
-                               ch.joint[0].v[0], ch.joint[0].v[1], ch.joint[0].v[2]};
-        emit(0, col);
-    }
-    screw_exp(ch.joint[0], q[0], P);
 #pragma unroll
-    for (int i = 1; i < NJ; i++)
+    for (int i = 0; i < NJ; i++)
     {
-        if (WANT_J)
+        const bool first = i == 0, advance = WANT_T || i < NJ - 1;
+        switch (ch.joint[i].kind)
         {
-            double col[6];
-            rigid_adjoint_apply(P, ch.joint[i].w, ch.joint[i].v, col);
-            emit(i, col);
-        }
-        if (WANT_T || i < NJ - 1)
-        {
-            Rigid E, Q;
-            screw_exp(ch.joint[i], q[i], E);
-            rigid_mul(P, E, Q);
-            P = Q;
+        case 1: poe_joint<1>(ch.joint[i], q[i], P, i, first, WANT_J, advance, emit); break;
+        case 2: poe_joint<2>(ch.joint[i], q[i], P, i, first, WANT_J, advance, emit); break;
+        case 3: poe_joint<3>(ch.joint[i], q[i], P, i, first, WANT_J, advance, emit); break;
+        default: poe_joint<0>(ch.joint[i], q[i], P, i, first, WANT_J, advance, emit); break;
         }
     }
     if (WANT_T)
@@ -830,17 +976,19 @@ PPX_DEV void jacobi_cs(double a, double b, double g, double &c, double &s)
     c = u * w;
     s = (d >= 0.0 ? g2 : -g2) * w;
 }
-// ... and the tangent as well (the two-sided update of the diagonal needs it)
-PPX_DEV void jacobi_cst(double a, double b, double g, double &c, double &s, double &t)
+// ... and the tangent as well (the two-sided update of the diagonal needs it); T = double, or float for the
+// preconditioning sweeps
+template <class T>
+PPX_DEV void jacobi_cst(T a, T b, T g, T &c, T &s, T &t)
 {
-    const double d = b - a;
-    const double g2 = g + g;
-    const double gg = g2 * g2;
-    const double r = fma(d, d, gg);
-    const double h = r * rsqrt_nr(r);
-    const double u = fabs(d) + h;
-    const double w = rsqrt_nr(fma(u, u, gg));
-    const double sg = d >= 0.0 ? g2 : -g2;
+    const T d = b - a;
+    const T g2 = g + g;
+    const T gg = g2 * g2;
+    const T r = t_fma(d, d, gg);
+    const T h = r * rsqrt_nr(r);
+    const T u = t_abs(d) + h;
+    const T w = rsqrt_nr(t_fma(u, u, gg));
+    const T sg = d >= T(0) ? g2 : -g2;
     c = u * w;
     s = sg * w;
     t = sg * rcp_nr(u);
@@ -869,38 +1017,38 @@ constexpr double SVD_FINE_COS2 = 1e-10;
 
 // One rotation of the one-sided Jacobi SVD on the columns at positions p and p+1, derived in two phases so that
 // the rotations of a round (disjoint positions) can be derived together: their chains are independent and overlap.
-template <int M>
-PPX_DEV void svd_pair_derive(const double (&ap)[M], const double (&aq)[M], double &np_, double &nq_, double tol2,
-                             double &c, double &s, bool &act, bool &coarse)
+template <int M, class T>
+PPX_DEV void svd_pair_derive(const T (&ap)[M], const T (&aq)[M], T &np_, T &nq_, T tol2, T fine2, T &c, T &s, bool &act,
+                             bool &coarse)
 {
-    double ga = 0.0;
+    T ga = T(0);
 #pragma unroll
     for (int i = 0; i < M; i++)
-        ga = fma(ap[i], aq[i], ga);
-    const double g2 = ga * ga, nn = np_ * nq_;
+        ga = t_fma(ap[i], aq[i], ga);
+    const T g2 = ga * ga, nn = np_ * nq_;
     act = g2 > tol2 * nn;
-    coarse |= g2 > SVD_FINE_COS2 * nn;
-    double t;
-    jacobi_cst(np_, nq_, ga, c, s, t);
-    c = act ? c : 1.0;
-    s = act ? s : 0.0;
-    t = act ? t : 0.0;
+    coarse |= g2 > fine2 * nn;
+    T t;
+    jacobi_cst<T>(np_, nq_, ga, c, s, t);
+    c = act ? c : T(1);
+    s = act ? s : T(0);
+    t = act ? t : T(0);
     // the rotated columns SWAP positions (odd-even transposition ordering): so do their norms
-    const double n0 = fma(-t, ga, np_), n1 = fma(t, ga, nq_);
+    const T n0 = t_fma(-t, ga, np_), n1 = t_fma(t, ga, nq_);
     np_ = n1;
     nq_ = n0;
 }
 
 // x' = c x - s y,  y' = s x + c y, stored swapped: position p gets y', position p+1 gets x'
-template <int L>
-PPX_DEV void rotate_swap(double (&xp)[L], double (&xq)[L], double c, double s)
+template <int L, class T>
+PPX_DEV void rotate_swap(T (&xp)[L], T (&xq)[L], T c, T s)
 {
 #pragma unroll
     for (int i = 0; i < L; i++)
     {
-        const double x = xp[i], y = xq[i];
-        xp[i] = fma(s, x, c * y);
-        xq[i] = fma(c, x, -s * y);
+        const T x = xp[i], y = xq[i];
+        xp[i] = t_fma(s, x, c * y);
+        xq[i] = t_fma(c, x, -s * y);
     }
 }
 
@@ -917,18 +1065,17 @@ PPX_DEV void swap_cols(double (&xp)[L], double (&xq)[L])
 }
 
 // One round of the odd-even ordering: positions (START, START+1), (START+2, START+3), ...
-template <int M, int N, int START, bool WANT_V, bool WANT_C>
-PPX_DEV void svd_round(double (&a)[N][M], double (&v)[N][N], double (&cv)[N], double (&nrm)[N], double tol2,
-                       bool &rotated, bool &coarse)
+template <int M, int N, int START, bool WANT_V, bool WANT_C, class T>
+PPX_DEV void svd_round(T (&a)[N][M], T (&v)[N][N], T (&cv)[N], T (&nrm)[N], T tol2, T fine2, bool &rotated, bool &coarse)
 {
     constexpr int P = (N - START) / 2;
-    double c[P > 0 ? P : 1], s[P > 0 ? P : 1];
+    T c[P > 0 ? P : 1], s[P > 0 ? P : 1];
     bool act[P > 0 ? P : 1];
 #pragma unroll
     for (int k = 0; k < P; k++)
     {
-        svd_pair_derive<M>(a[START + 2 * k], a[START + 2 * k + 1], nrm[START + 2 * k], nrm[START + 2 * k + 1], tol2,
-                           c[k], s[k], act[k], coarse);
+        svd_pair_derive<M, T>(a[START + 2 * k], a[START + 2 * k + 1], nrm[START + 2 * k], nrm[START + 2 * k + 1], tol2,
+                              fine2, c[k], s[k], act[k], coarse);
         rotated |= act[k];
     }
 #pragma unroll
@@ -937,15 +1084,172 @@ PPX_DEV void svd_round(double (&a)[N][M], double (&v)[N][N], double (&cv)[N], do
         // always applied, also when no lane needs it (c = 1, s = 0 is then the plain swap): a warp-uniform skip
         // would save the multiply-adds of the last sweep but costs register moves at every merge point of the
         // rolled loop -- measured slower
-        rotate_swap<M>(a[START + 2 * k], a[START + 2 * k + 1], c[k], s[k]);
+        rotate_swap<M, T>(a[START + 2 * k], a[START + 2 * k + 1], c[k], s[k]);
         if (WANT_V)
-            rotate_swap<N>(v[START + 2 * k], v[START + 2 * k + 1], c[k], s[k]);
+            rotate_swap<N, T>(v[START + 2 * k], v[START + 2 * k + 1], c[k], s[k]);
         if (WANT_C) // a vector with one entry per column, carried through the same rotations
         {
-            const double x = cv[START + 2 * k], y = cv[START + 2 * k + 1];
-            cv[START + 2 * k] = fma(s[k], x, c[k] * y);
-            cv[START + 2 * k + 1] = fma(c[k], x, -s[k] * y);
+            const T x = cv[START + 2 * k], y = cv[START + 2 * k + 1];
+            cv[START + 2 * k] = t_fma(s[k], x, c[k] * y);
+            cv[START + 2 * k + 1] = t_fma(c[k], x, -s[k] * y);
         }
+    }
+}
+
+// ---- packed single precision (sm_100: FFMA2 / FMUL2 do two fp32 operations per issue slot) ----------------------
+#ifdef __CUDA_ARCH__
+typedef float2 F2;
+PPX_DEV F2 f2_fma(F2 a, F2 b, F2 c) { return __ffma2_rn(a, b, c); }
+PPX_DEV F2 f2_mul(F2 a, F2 b) { return __fmul2_rn(a, b); }
+#else
+struct F2
+{
+    float x, y;
+};
+PPX_DEV F2 f2_fma(F2 a, F2 b, F2 c) { return F2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+PPX_DEV F2 f2_mul(F2 a, F2 b) { return F2{a.x * b.x, a.y * b.y}; }
+#endif
+PPX_DEV F2 f2_set(float x, float y)
+{
+    F2 r;
+    r.x = x, r.y = y;
+    return r;
+}
+
+// Single-precision preconditioner of the Jacobi SVD.  The fp64 pipe is what bounds these kernels (64 DFMA per clock
+// and SM against 128 FFMA, and a packed FFMA2 does two of those per issue slot), and most of a Jacobi SVD's arithmetic
+// is spent getting NEAR the answer: the first 3-4 of its ~5 sweeps.  So those are run on a float copy of the matrix
+// (same odd-even ordering, fixed even number of sweeps, no votes; rows held in pairs so that dot products and
+// rotations are FFMA2 / FMUL2), only to produce the accumulated rotations V0 ~ the right singular vectors to ~1e-6.
+// V0 is then made orthonormal to fp64 accuracy by modified Gram-Schmidt (it is nearly orthogonal, so MGS loses
+// nothing), and the fp64 iteration starts from A V0 with V = V0: 2 sweeps instead of 5 (measured on the host build,
+// tools/svd_sweeps.cpp).  Every number that leaves the kernel is computed by the fp64 iteration with its own
+// convergence test -- the preconditioner can only change how many sweeps that takes, not what it converges to.
+// (fp32 range: the copy is scaled by an exact power of two so that the largest entry is in [1, 2); entries 2^-126
+// below it flush to zero, which a preconditioner may ignore.)
+template <int MH, int NH>
+PPX_DEV void f32_rotate_pair(F2 (&ap)[MH], F2 (&aq)[MH], F2 (&vp)[NH], F2 (&vq)[NH], float &np_, float &nq_, float tol2)
+{
+    F2 acc = f2_set(0.0f, 0.0f);
+#pragma unroll
+    for (int i = 0; i < MH; i++)
+        acc = f2_fma(ap[i], aq[i], acc);
+    const float ga = acc.x + acc.y;
+    const bool act = ga * ga > tol2 * (np_ * nq_);
+    float c, s, t;
+    jacobi_cst<float>(np_, nq_, ga, c, s, t);
+    c = act ? c : 1.0f;
+    s = act ? s : 0.0f;
+    t = act ? t : 0.0f;
+    const float n0 = fmaf(-t, ga, np_), n1 = fmaf(t, ga, nq_);
+    np_ = n1; // the rotated columns swap positions
+    nq_ = n0;
+    const F2 c2 = f2_set(c, c), s2 = f2_set(s, s), ns2 = f2_set(-s, -s);
+#pragma unroll
+    for (int i = 0; i < MH; i++)
+    {
+        const F2 x = ap[i], y = aq[i];
+        ap[i] = f2_fma(s2, x, f2_mul(c2, y));
+        aq[i] = f2_fma(c2, x, f2_mul(ns2, y));
+    }
+#pragma unroll
+    for (int i = 0; i < NH; i++)
+    {
+        const F2 x = vp[i], y = vq[i];
+        vp[i] = f2_fma(s2, x, f2_mul(c2, y));
+        vq[i] = f2_fma(c2, x, f2_mul(ns2, y));
+    }
+}
+
+template <int M, int N>
+PPX_DEV void jacobi_precondition_f32(const double (&a64)[N][M], double (&v0)[N][N])
+{
+#ifndef PPX_SVD_F32_SWEEPS
+#define PPX_SVD_F32_SWEEPS 4
+#endif
+    constexpr int SWEEPS = PPX_SVD_F32_SWEEPS; // even: the odd-even ordering reverses the column order every sweep
+    static_assert(SWEEPS % 2 == 0, "an odd number of sweeps would leave the columns reversed");
+    constexpr int MH = (M + 1) / 2, NH = (N + 1) / 2; // rows in pairs; an odd count is padded with a zero row
+    int mexp = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++)
+#pragma unroll
+        for (int i = 0; i < M; i++)
+            mexp = max(mexp, __double2hiint(a64[j][i]) & 0x7ff00000);
+    // 2^-(e) with e = exponent of the largest entry; left at 1 for zero / denormal-only / inf / NaN matrices
+    const int e = (mexp >> 20) - 1023;
+    const bool scalable = mexp != 0 && mexp != 0x7ff00000 && e > -1000 && e < 1000;
+    const double sc = scalable ? __hiloint2double((1023 - e) << 20, 0) : 1.0;
+    F2 a[N][MH], v[N][NH];
+    float nrm[N];
+#pragma unroll
+    for (int j = 0; j < N; j++)
+    {
+#pragma unroll
+        for (int i = 0; i < MH; i++)
+            a[j][i] = f2_set((float)(a64[j][2 * i] * sc), 2 * i + 1 < M ? (float)(a64[j][2 * i + 1 < M ? 2 * i + 1 : 0] * sc) : 0.0f);
+#pragma unroll
+        for (int i = 0; i < NH; i++)
+            v[j][i] = f2_set(2 * i == j ? 1.0f : 0.0f, 2 * i + 1 == j ? 1.0f : 0.0f);
+    }
+    constexpr float TOL2 = 16.0f * M * 1.4210855e-14f; // (4 sqrt(M) eps_f)^2, eps_f = 2^-23
+#pragma unroll 1
+    for (int sweep = 0; sweep < SWEEPS; sweep++)
+    {
+#pragma unroll
+        for (int j = 0; j < N; j++)
+        {
+            F2 acc = f2_set(0.0f, 0.0f);
+#pragma unroll
+            for (int i = 0; i < MH; i++)
+                acc = f2_fma(a[j][i], a[j][i], acc);
+            nrm[j] = acc.x + acc.y;
+        }
+#pragma unroll 1
+        for (int it = 0; it < N / 2; it++)
+        {
+#pragma unroll
+            for (int k = 0; k + 1 < N; k += 2)
+                f32_rotate_pair<MH, NH>(a[k], a[k + 1], v[k], v[k + 1], nrm[k], nrm[k + 1], TOL2);
+#pragma unroll
+            for (int k = 1; k + 1 < N; k += 2)
+                f32_rotate_pair<MH, NH>(a[k], a[k + 1], v[k], v[k + 1], nrm[k], nrm[k + 1], TOL2);
+        }
+        if (N & 1)
+        {
+#pragma unroll
+            for (int k = 0; k + 1 < N; k += 2)
+                f32_rotate_pair<MH, NH>(a[k], a[k + 1], v[k], v[k + 1], nrm[k], nrm[k + 1], TOL2);
+        }
+    }
+    // V0 in fp64, orthonormalised by modified Gram-Schmidt (an even number of sweeps left the columns in order)
+#pragma unroll
+    for (int j = 0; j < N; j++)
+    {
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            v0[j][i] = (double)((i & 1) ? v[j][i / 2].y : v[j][i / 2].x);
+#pragma unroll
+        for (int k = 0; k < j; k++)
+        {
+            double r = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                r = fma(v0[k][i], v0[j][i], r);
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                v0[j][i] = fma(-r, v0[k][i], v0[j][i]);
+        }
+        double n2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            n2 = fma(v0[j][i], v0[j][i], n2);
+        // a NaN / inf input poisons the float sweeps: fall back to the identity column rather than spreading NaN
+        const bool good = n2 > 0.25 && n2 < 4.0;
+        const double inv = rsqrt_nr(good ? n2 : 1.0);
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            v0[j][i] = good ? v0[j][i] * inv : ((i == j) ? 1.0 : 0.0);
     }
 }
 
@@ -964,6 +1268,12 @@ PPX_DEV void svd_round(double (&a)[N][M], double (&v)[N][N], double (&cv)[N], do
 // sqrt(M) eps; the singular values come out with relative accuracy ~ tol).  Sweeps stop when a whole sweep
 // rotated nothing in any lane of the warp.  Squared column norms are recomputed at the start of every sweep and
 // carried through its rotations (a rotation by tangent t moves t*gamma from one norm to the other).
+#ifdef PPX_SVD_COUNT_SWEEPS
+static long g_ppx_svd_sweeps = 0;
+#endif
+#ifndef PPX_SVD_PRECOND
+#define PPX_SVD_PRECOND 1 // single-precision preconditioning sweeps (jacobi_precondition_f32); 0: fp64 from the start
+#endif
 template <int M, int N, bool WANT_V, bool WANT_C = false>
 PPX_DEV void jacobi_svd_core(double (&A)[M * N], double (&V)[N * N], double (&w2)[N], double *carry = nullptr)
 {
@@ -981,6 +1291,46 @@ PPX_DEV void jacobi_svd_core(double (&A)[M * N], double (&V)[N * N], double (&w2
         for (int i = 0; i < N; i++)
             v[j][i] = (i == j) ? 1.0 : 0.0;
     }
+#if PPX_SVD_PRECOND
+    if (N >= 3)
+    {
+        // start the fp64 iteration from A V0, V = V0 (and the carried vector from V0^T carry)
+        jacobi_precondition_f32<M, N>(a, v);
+        double t[N][M];
+#pragma unroll
+        for (int j = 0; j < N; j++)
+#pragma unroll
+            for (int i = 0; i < M; i++)
+            {
+                double acc = a[0][i] * v[j][0];
+#pragma unroll
+                for (int k = 1; k < N; k++)
+                    acc = fma(a[k][i], v[j][k], acc);
+                t[j][i] = acc;
+            }
+        if (WANT_C)
+        {
+            double tc[N];
+#pragma unroll
+            for (int j = 0; j < N; j++)
+            {
+                double acc = cv[0] * v[j][0];
+#pragma unroll
+                for (int k = 1; k < N; k++)
+                    acc = fma(cv[k], v[j][k], acc);
+                tc[j] = acc;
+            }
+#pragma unroll
+            for (int j = 0; j < N; j++)
+                cv[j] = tc[j];
+        }
+#pragma unroll
+        for (int j = 0; j < N; j++)
+#pragma unroll
+            for (int i = 0; i < M; i++)
+                a[j][i] = t[j][i];
+    }
+#endif
     constexpr double TOL2 = 16.0 * M * EPS_DP * EPS_DP;
     constexpr int MAX_SWEEPS = 12;
     bool reversed = false;
@@ -999,12 +1349,15 @@ PPX_DEV void jacobi_svd_core(double (&A)[M * N], double (&V)[N * N], double (&w2
 #pragma unroll 1
         for (int it = 0; it < N / 2; it++)
         {
-            svd_round<M, N, 0, WANT_V, WANT_C>(a, v, cv, nrm, TOL2, rotated, coarse);
-            svd_round<M, N, 1, WANT_V, WANT_C>(a, v, cv, nrm, TOL2, rotated, coarse);
+            svd_round<M, N, 0, WANT_V, WANT_C, double>(a, v, cv, nrm, TOL2, SVD_FINE_COS2, rotated, coarse);
+            svd_round<M, N, 1, WANT_V, WANT_C, double>(a, v, cv, nrm, TOL2, SVD_FINE_COS2, rotated, coarse);
         }
         if (N & 1)
-            svd_round<M, N, 0, WANT_V, WANT_C>(a, v, cv, nrm, TOL2, rotated, coarse);
+            svd_round<M, N, 0, WANT_V, WANT_C, double>(a, v, cv, nrm, TOL2, SVD_FINE_COS2, rotated, coarse);
         reversed = !reversed;
+#ifdef PPX_SVD_COUNT_SWEEPS // host-side instrumentation of tests/cpp (never defined for the device build)
+        g_ppx_svd_sweeps++;
+#endif
         if (!__any_sync(0xffffffffu, rotated))
             break;
 #ifndef PPX_SVD_NO_LOOKAHEAD
@@ -1140,6 +1493,28 @@ PPX_DEV void jacobi_rowsolve(const double (&A)[N * N], const double (&b)[N], dou
 // before truncation could matter; false for zero, inf and NaN pivots -- the row-orthogonalising Jacobi solve is run as
 // well and its result taken for those lanes.  The decision to run it is per warp, so well-conditioned batches never
 // execute it.  `allow_lu = false` forces the Jacobi path.
+// The Jacobi fallback as an out-of-line function (-DPPX_PINV_COLD=1).  Tried and measured on the IK Newton step: the
+// registers that are live across the call get spilled around it and the common path pays for that -- 8.7 G inst/s
+// against 10.0 G with the fallback inlined -- so it is off.
+#ifndef PPX_PINV_COLD
+#define PPX_PINV_COLD 0
+#endif
+template <int N>
+__device__ __noinline__ void jacobi_rowsolve_cold(const double *A, const double *b, double *x)
+{
+    double a[N * N], rhs[N], sol[N];
+#pragma unroll
+    for (int i = 0; i < N * N; i++)
+        a[i] = A[i];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        rhs[i] = b[i];
+    jacobi_rowsolve<N>(a, rhs, sol);
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        x[i] = sol[i];
+}
+
 template <int N>
 PPX_DEV void square_pinv_solve(const double (&A)[N * N], const double (&b)[N], double (&x)[N], bool allow_lu)
 {
@@ -1167,7 +1542,20 @@ PPX_DEV void square_pinv_solve(const double (&A)[N * N], const double (&b)[N], d
         }
     }
     double xs[N];
+#if PPX_PINV_COLD
+    {
+        double Ac[N * N], bc[N];
+#pragma unroll
+        for (int i = 0; i < N * N; i++)
+            Ac[i] = A[i];
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            bc[i] = b[i];
+        jacobi_rowsolve_cold<N>(Ac, bc, xs);
+    }
+#else
     jacobi_rowsolve<N>(A, b, xs);
+#endif
 #pragma unroll
     for (int i = 0; i < N; i++)
         x[i] = easy ? rx[i] : xs[i];

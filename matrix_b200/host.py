@@ -70,6 +70,20 @@ def copy_probe(host_array, direction, seconds=1.0):
     return [out[i] for i in range(n)]
 
 
+def tune_devices(candidates, host_array, direction, seconds=0.15):
+    """ppx_cuda_host_tune_devices: pick the subset of `candidates` (None: all visible devices) whose host links carry
+    the most together and make it the device list -> (devices, aggregate GB/s)"""
+    d = {"h2d": 0, "d2h": 1, "both": 2}[direction]
+    agg = C.c_double(0.0)
+    if candidates is None:
+        arr, cnt = None, 0
+    else:
+        arr, cnt = (C.c_int * len(candidates))(*[int(x) for x in candidates]), len(candidates)
+    check(lib.ppx_cuda_host_tune_devices(arr, cnt, C.c_void_p(host_array.ctypes.data), host_array.nbytes, d,
+                                         float(seconds), C.byref(agg)))
+    return get_devices(), agg.value
+
+
 def _p(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 

@@ -91,6 +91,21 @@ def make_ops(layout=mb.SOA):
         return lambda: mb.SE3_mul(T, T2, layout=layout, out=o)
     ops.append(Op("SE3_mul", 1 << 24, 8 * 48, setup_mul, "liegroup.hpp:204-207", 8 * (48 if aos else 40)))
 
+    def matmul_op(m, n_, l):  # MatrixS::operator*
+        def setup(cnt, dev):
+            A = _rec(cnt, m * n_, 0x301, -1.0, 1.0, dev)
+            B = _rec(cnt, n_ * l, 0x302, -1.0, 1.0, dev)
+            if not aos:
+                A, B = mb.to_soa(A), mb.to_soa(B)
+            o = out(m * l, cnt, dev)
+            return lambda: mb.matmul(m, n_, l, A, B, layout=layout, out=o)
+        ops.append(Op(f"matmul_{m}x{n_}x{l}", 1 << 24, 8 * (m * n_ + n_ * l + m * l), setup, "matrixs.hpp:596-640"))
+
+    matmul_op(3, 3, 3)
+    matmul_op(4, 4, 4)
+    matmul_op(6, 6, 6)
+    matmul_op(6, 6, 1)
+
     def setup_jac(n, dev):
         w = lay(_lie(n, dev)[3])
         o = out(9, n, dev)

@@ -230,6 +230,31 @@ def test_fk_jacobian_recorded_reference_and_other_chains(mb, fixtures):
             assert rel_err(Js, fixtures[f"chain{nj}.Js"]).max() < REL
 
 
+def test_mixed_axis_aligned_and_general_chain(mb, cpu_ref):
+    """axis-aligned joints take the structured kernel path (poe_joint<1..3>), all others the general one: a chain
+    mixing both, incl. a negative axis, a prismatic joint and a non-unit axis, FK + Jacobian and the IK Newton step"""
+    from test_math_host import MIXED_CHAIN, MIXED_HOME
+    n = 20011
+    q = synth.joint_angles(n, seed=0xC4A2)
+    q[:64, 0] = 0.0
+    q[64:128, 2] = 1e-9
+    q[128:192, 1] = 1e-9
+    kin = mb.Kinematics(MIXED_CHAIN, MIXED_HOME)
+    rT, rJ = cpu_ref.poe_fk_jacobian(MIXED_CHAIN, MIXED_HOME, q)
+    for layout in LAYOUTS:
+        T, Js = run(mb, kin.fk_jacobian, layout, q)
+        assert rel_err(T, rT).max() < REL and rel_err(Js, rJ).max() < REL
+    Tt = cpu_ref.poe_fk_jacobian(MIXED_CHAIN, MIXED_HOME, q + synth.ik_offsets(n), want_Js=False)[0]
+    qo, Vs = run(mb, kin.ik_newton_step, "soa", q, Tt, want_Vs=True)
+    rq, rV = cpu_ref.ik_newton_step(MIXED_CHAIN, MIXED_HOME, q, Tt)
+    assert rel_err(Vs, rV).max() < REL
+    sv = np.linalg.svd(rJ.reshape(n, 6, 6), compute_uv=False)
+    kappa = sv[:, 0] / sv[:, -1]
+    err = np.abs((qo - q) - (rq - q)).max(axis=1) / np.maximum(np.abs(rq - q).max(axis=1), 1e-300)
+    ok = kappa < 1e6
+    assert ok.mean() > 0.9 and np.all(err[ok] <= REL * np.maximum(1.0, kappa[ok]))
+
+
 def test_golden_ur5(mb, golden):
     g = golden["ur5"]
     kin = mb.Kinematics(np.array(g["screws"], dtype=float), np.array(g["home"]))
@@ -1040,6 +1065,9 @@ def test_host_face_device_list(mb):
     assert host.get_devices() == []
     rates = host.copy_probe(q, "d2h", 0.2)
     assert len(rates) == 1 and rates[0] > 1.0  # GB/s
+    devs, agg = host.tune_devices([0], q, "d2h", 0.05)  # one candidate: it is chosen, and becomes the device list
+    assert devs == [0] and host.get_devices() == [0] and agg > 1.0
+    host.set_devices(None)
 
 
 def test_two_device_host_call_is_bitwise_the_one_device_result(mb, port):

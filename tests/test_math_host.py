@@ -190,3 +190,33 @@ def test_device_lie_maps_and_kinematics_on_the_host(mh, port, fixtures):
     Tq, Js = np.empty((q.shape[0], 16)), np.empty((q.shape[0], 36))
     assert mh.mh_fk_jacobian6(_p(S), _p(M), _p(q), _p(Tq), _p(Js), C.c_size_t(q.shape[0])) == 0
     assert np.abs(Tq - fixtures["ur5.T"]).max() < 1e-14 and np.abs(Js - fixtures["ur5.Js"]).max() < 1e-14
+
+
+MIXED_CHAIN = np.array([
+    [0.0, 0.0, 1.0, 0.0, 0.0, 0.0],            # revolute about +z        (aligned)
+    [0.3, -0.5, 0.8, 0.2, -0.1, 0.4],          # general screw, |w| != 1
+    [0.0, -1.0, 0.0, -0.089, 0.0, 0.425],      # revolute about -y        (aligned, negative sign)
+    [0.0, 0.0, 0.0, 0.0, 0.6, 0.8],            # prismatic (w = 0)
+    [1.0, 0.0, 0.0, 0.0, 0.3, -0.2],           # revolute about +x        (aligned)
+    [0.0, 2.0, 0.0, 0.1, 0.0, 0.3],            # along y but not unit: general path
+])
+MIXED_HOME = np.array([0.0, 1.0, 0.0, 0.0, -1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.3, -0.2, 0.5, 1.0])
+
+
+def test_axis_aligned_and_general_joints_mix_on_the_host(mh, port):
+    """poe_joint: joints whose axis is a unit coordinate axis take the structured path, everything else the general
+    one -- a chain that mixes both (incl. a negative axis, a prismatic joint and a non-unit axis) against the oracle,
+    with angles that hit the |x| < EPS_SP identity branch of se3::exp on aligned and general joints alike"""
+    n = 4096
+    q = synth.joint_angles(n, seed=0xC4A1)
+    q[:64, 0] = 0.0
+    q[64:128, 2] = 1e-9
+    q[128:192, 1] = 1e-9
+    q[192:256, 4] = -5e-8
+    q = np.ascontiguousarray(q)
+    T, Js = np.empty((n, 16)), np.empty((n, 36))
+    assert mh.mh_fk_jacobian6(_p(MIXED_CHAIN), _p(MIXED_HOME), _p(q), _p(T), _p(Js), C.c_size_t(n)) == 0
+    rT, rJ = port.poe_fk_jacobian(MIXED_CHAIN, MIXED_HOME, q)
+    assert (np.abs(T - rT).max(axis=1) / np.abs(rT).max(axis=1)).max() < 1e-12
+    assert (np.abs(Js - rJ).max(axis=1) / np.abs(rJ).max(axis=1)).max() < 1e-12
+    assert np.all(T[:, [3, 7, 11]] == 0.0) and np.all(T[:, 15] == 1.0)

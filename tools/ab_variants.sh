@@ -6,7 +6,7 @@ cp matrix_b200/libppx_cuda.so /tmp/libppx_cuda.orig.so
 for v in "$@"; do
   cp build/variants/$v.so matrix_b200/libppx_cuda.so
   echo "== $v"
-  python bench.py --workload $WL --n $N --no-others --no-cpu --no-e2e --steps 5 --warmup 3 2>&1 | python -c "
+  python bench.py --workload $WL $( [ "$N" != "0" ] && echo --n $N ) --no-others --no-cpu --no-e2e --steps 5 --warmup 3 2>&1 | python -c "
 import sys,json
 for line in sys.stdin:
     line=line.strip()
