@@ -287,8 +287,10 @@ done:
     host_release(device, nslots, st, rc == PPX_OK);
 }
 
+// chunk_mult: ops whose kernels have a long per-launch tail (the persistent trust-region / Newton-loop kernels: the
+// last stalled instance of a launch ends ~9 ms after the queue has drained) ask for larger chunks
 template <class Run>
-int pipeline(const std::vector<HostIn> &ins, const std::vector<HostOut> &outs, size_t n, Run run)
+int pipeline(const std::vector<HostIn> &ins, const std::vector<HostOut> &outs, size_t n, Run run, size_t chunk_mult = 1)
 {
     if (n == 0)
         return PPX_OK;
@@ -301,7 +303,7 @@ int pipeline(const std::vector<HostIn> &ins, const std::vector<HostOut> &outs, s
     for (const HostOut &a : outs)
         out_b += a.ptr ? a.bytes : 0;
     const size_t widest = std::max<size_t>(std::max(in_b, out_b), 1);
-    size_t chunk = std::max<size_t>(env_chunk_bytes() / widest, 1024);
+    size_t chunk = std::max<size_t>(env_chunk_bytes() * chunk_mult / widest, 1024);
     chunk = (chunk + 1023) / 1024 * 1024;
     chunk = std::min(chunk, n);
 
@@ -803,7 +805,8 @@ int ppx_cuda_host_ik_codo(const double *screws, const double *home, int njoints,
                     [=](size_t c, void **i, void **o, void *s) {
                         return ppx_cuda_batch_ik_codo(screws, home, njoints, lo, hi, (cd)i[0], (cd)i[1], (md)o[0], (md)o[1],
                                                       (md)o[2], (int8_t *)o[3], c, PPX_LAYOUT_AOS, 0, s);
-                    });
+                    },
+                    16);
 }
 
 } // extern "C"

@@ -79,14 +79,14 @@ struct OpFkJacobian
 };
 
 // dq = linsolve<SVD>(Js, Vs).x: a square Jacobian (6 joints) needs no V, and no SVD either unless it is close to
-// singular (square_pinv_solve)
-template <int NJ>
+// singular (square_pinv_solve).  PRECOND selects the single-precision preconditioning of the Jacobi fallback.
+template <int NJ, bool PRECOND>
 __device__ __forceinline__ typename std::enable_if<NJ == 6>::type svd_solve_dispatch(double (&js)[36], const double (&vs)[6],
                                                                                     double (&dq)[6], bool allow_lu)
 {
-    square_pinv_solve<6>(js, vs, dq, allow_lu);
+    square_pinv_solve<6, PRECOND>(js, vs, dq, allow_lu);
 }
-template <int NJ>
+template <int NJ, bool PRECOND>
 __device__ __forceinline__ typename std::enable_if<NJ != 6>::type svd_solve_dispatch(double (&js)[6 * NJ],
                                                                                     const double (&vs)[6], double (&dq)[NJ],
                                                                                     bool)
@@ -96,12 +96,13 @@ __device__ __forceinline__ typename std::enable_if<NJ != 6>::type svd_solve_disp
     jacobi_svd_solve<6, NJ>(js, V, w2, vs, dq);
 }
 
-// Js(q) and Vs = Ad(T(q)) log(T(q)^-1 Tt)  (test/lie_test.cpp:104-108)
-template <int NJ>
-__device__ __forceinline__ void ik_residual(const ChainConst<NJ> &ch, const Rigid &target, const double (&q)[NJ],
-                                            double (&js)[6 * NJ], double (&vs)[6])
+// Vs = Ad(T(q)) log(T(q)^-1 Tt),  dq = pinv(Js(q)) Vs  (test/lie_test.cpp:104-110)
+template <int NJ, bool PRECOND = true>
+__device__ __forceinline__ void ik_newton_update(const ChainConst<NJ> &ch, const Rigid &target, double (&q)[NJ],
+                                                 double (&vs)[6], bool allow_lu)
 {
     Rigid t, ti, x;
+    double js[6 * NJ];
     poe_fk_jacobian<NJ, true, true>(ch, q, t, [&](int col, const double(&v)[6]) {
 #pragma unroll
         for (int k = 0; k < 6; k++)
@@ -113,47 +114,37 @@ __device__ __forceinline__ void ik_residual(const ChainConst<NJ> &ch, const Rigi
     SE3_log(x, lg);
     const double lw[3] = {lg[0], lg[1], lg[2]}, lv[3] = {lg[3], lg[4], lg[5]};
     rigid_adjoint_apply(t, lw, lv, vs);
-}
-
-// q <- q + pinv(Js(q)) Vs, the whole step in one thread (the Newton loop ik_solve_kernel uses this form)
-template <int NJ>
-__device__ __forceinline__ void ik_newton_update(const ChainConst<NJ> &ch, const Rigid &target, double (&q)[NJ],
-                                                 double (&vs)[6], bool allow_lu)
-{
-    double js[6 * NJ];
-    ik_residual<NJ>(ch, target, q, js, vs);
     double dq[NJ];
-    svd_solve_dispatch<NJ>(js, vs, dq, allow_lu);
+    svd_solve_dispatch<NJ, PRECOND>(js, vs, dq, allow_lu);
 #pragma unroll
     for (int i = 0; i < NJ; i++)
         q[i] += dq[i];
 }
 
-// BASELINE config 5, 48 + 128 B in, 48 B out.  Two kernels for the 6-joint step (ik_step_n):
-//
-//   OpIkStepLU   the step with the square pseudo-inverse solve done by LU with partial pivoting -- valid whenever the
-//                rigorous condition bound read off the factors stays below 1e10 (square_pinv_solve's argument).  A lane
-//                whose system fails that test marks its instance in a byte map.  No Jacobi code in this kernel: the
-//                common path keeps its own register allocation and instruction footprint.
-//   OpIkStepSvd  the step with the Jacobi SVD solve (the reference's truncation).  With a byte map it is the second
-//                pass: a warp looks at its 32 marks and, if none is set, is done; otherwise it recomputes its 32
-//                instances and replaces the marked ones.  Without a map (ppx_cuda_set_square_solve_lu(0), or fewer
-//                than 6 joints, a genuine least-squares problem) it is the whole step.
+// BASELINE config 5.  48 + 128 B in, 48 B out.  Two instantiations per chain length:
+//   SVD_ONLY = false  the common form: for 6 joints the square solve goes through LU with partial pivoting whenever the
+//                     rigorous condition bound allows (square_pinv_solve), with the Jacobi solve as the per-warp
+//                     fallback; 3 CTAs per SM (168 registers), inputs of the next tile staged with cp.async.
+//   SVD_ONLY = true   the Jacobi SVD solve on every instance (ppx_cuda_set_square_solve_lu(0): the step exactly as
+//                     north_star words it): 2 CTAs per SM (255 registers), no single-precision preconditioning --
+//                     the square solve accumulates no V, so the preconditioner's V0 costs more than it saves here.
+// Measured on B200 (2^25 instances): 10.1 G inst/s / 2.13 G inst/s.  The register allocation of the common form is
+// fragile -- the same arithmetic with the fallback out of line, or split into an LU pass and an SVD pass over marked
+// instances, ran at 7.9-8.7 G inst/s -- so it is kept in the shape that measured best.
 #ifndef PPX_IK_MINB
 #define PPX_IK_MINB 3
 #endif
-struct OpIkStepLU
+template <int NJ, bool SVD_ONLY>
+struct OpIkStep
 {
-    static constexpr int NJ = 6;
-    static constexpr int BLOCK = 128, MINB = PPX_IK_MINB, MAXW = 16;
+    static constexpr int BLOCK = 128, MINB = SVD_ONLY ? 2 : PPX_IK_MINB, MAXW = 16;
     ChainConst<NJ> ch;
     const double *q;
     const double *Tt;
     double *q_out;
     double *Vs;
-    unsigned char *hard; // one byte per instance, zeroed before the launch
     // joint angles and target pose of the next tile staged (cp.async) behind the arithmetic of the current one
-    static constexpr bool PREFETCH = true;
+    static constexpr bool PREFETCH = !SVD_ONLY;
     static constexpr int IN_WIDTH = NJ + 16 + 2;
     template <class IO>
     __device__ __forceinline__ void prefetch(const IO &io, double *stage) const
@@ -164,77 +155,29 @@ struct OpIkStepLU
     template <class IO>
     __device__ __forceinline__ void compute_store(const IO &io, const double *stage) const
     {
-        double qi[NJ], m[16], js[36], vs[6], dq[NJ];
+        double qi[NJ], m[16];
         io.template read_staged<NJ>(stage, qi);
         io.template read_staged<16>(stage + IO::stage_doubles(BLOCK, NJ), m);
-        Rigid target;
-        rigid_from_record(m, target);
-        ik_residual<NJ>(ch, target, qi, js, vs);
-#pragma unroll
-        for (int i = 0; i < NJ; i++)
-            dq[i] = vs[i];
-        bool even;
-        double ipiv[NJ];
-        lu_factor_solve<NJ, 1>(js, dq, even, ipiv);
-        const bool easy = lu_cond_bound<NJ>(js, ipiv) < SQUARE_LU_COND_MAX;
-        // a marked instance leaves this pass with its ORIGINAL q in q_out: the second pass then needs q_out alone,
-        // so the call stays correct when q_out aliases q (in-place update)
-#pragma unroll
-        for (int i = 0; i < NJ; i++)
-            qi[i] = easy ? qi[i] + dq[i] : qi[i];
-        io.store(q_out, qi);
-        if (Vs != nullptr)
-            io.store(Vs, vs);
-        if (!easy && io.valid)
-            hard[io.i] = 1;
+        step_store(io, qi, m);
     }
-};
-
-template <int NJ>
-struct OpIkStepSvd
-{
-    static constexpr int BLOCK = 128, MINB = 2, MAXW = 16;
-    ChainConst<NJ> ch;
-    const double *q;
-    const double *Tt;
-    double *q_out;
-    double *Vs;
-    const unsigned char *hard; // nullptr: every instance
     template <class IO>
     __device__ __forceinline__ void operator()(const IO &io) const
     {
-        const bool mine = hard == nullptr || (io.valid && hard[io.i] != 0);
-        if (hard != nullptr && !__any_sync(0xffffffffu, mine))
-            return; // nothing marked among this warp's 32 instances
-        double qi[NJ], m[16], js[6 * NJ], vs[6], dq[NJ], prev[NJ], pvs[6];
-        // second pass: q_out holds the first pass's result -- the updated q of the unmarked lanes (kept), the original
-        // q of the marked ones (see OpIkStepLU); unmarked lanes run the arithmetic on whatever they hold (the Jacobi
-        // sweeps end by warp vote, every lane has to take part) and their values are dropped
-        io.load(hard != nullptr ? q_out : q, qi);
+        double qi[NJ], m[16];
+        io.load(q, qi);
         io.load(Tt, m);
-        if (hard != nullptr && Vs != nullptr)
-            io.load(Vs, pvs);
-#pragma unroll
-        for (int i = 0; i < NJ; i++)
-            prev[i] = qi[i];
+        step_store(io, qi, m);
+    }
+    template <class IO>
+    __device__ __forceinline__ void step_store(const IO &io, double (&qi)[NJ], const double (&m)[16]) const
+    {
+        double vs[6];
         Rigid target;
         rigid_from_record(m, target);
-        ik_residual<NJ>(ch, target, qi, js, vs);
-        svd_solve_dispatch<NJ>(js, vs, dq, false);
-#pragma unroll
-        for (int i = 0; i < NJ; i++)
-            qi[i] = mine ? qi[i] + dq[i] : prev[i];
+        ik_newton_update<NJ, !SVD_ONLY>(ch, target, qi, vs, !SVD_ONLY);
         io.store(q_out, qi);
         if (Vs != nullptr)
-        {
-            if (hard != nullptr)
-            {
-#pragma unroll
-                for (int i = 0; i < 6; i++)
-                    vs[i] = mine ? vs[i] : pvs[i];
-            }
             io.store(Vs, vs);
-        }
     }
 };
 
@@ -453,46 +396,15 @@ int fk_jacobian_n(const double *screws, const double *home, const double *q, dou
     return dispatch(layout, OpFkJacobian<NJ, false, true>{ch, q, nullptr, Js}, n, ld, stream);
 }
 
-// fewer than 6 joints: the Jacobi SVD step on every instance
 template <int NJ>
 int ik_step_n(const double *screws, const double *home, const double *q, const double *Tt, double *q_out,
               double *Vs, size_t n, int layout, size_t ld, void *stream)
 {
     ChainConst<NJ> ch;
     fold_chain<NJ>(screws, home, ch);
-    return dispatch(layout, OpIkStepSvd<NJ>{ch, q, Tt, q_out, Vs, nullptr}, n, ld, stream);
-}
-
-// 6 joints: the LU pass over everything, then the SVD pass over what the LU pass marked (see OpIkStepLU).  The byte
-// map lives for this call only (stream-ordered allocation from the library's retained pool).
-int ik_step_6(const double *screws, const double *home, const double *q, const double *Tt, double *q_out, double *Vs,
-              size_t n, int layout, size_t ld, void *stream)
-{
-    ChainConst<6> ch;
-    fold_chain<6>(screws, home, ch);
-    if (g_ppx_square_lu.load(std::memory_order_relaxed) == 0)
-        return dispatch(layout, OpIkStepSvd<6>{ch, q, Tt, q_out, Vs, nullptr}, n, ld, stream);
-    if (layout != PPX_LAYOUT_AOS && layout != PPX_LAYOUT_SOA)
-        return PPX_ERR_BAD_LAYOUT;
-    int device = 0;
-    cudaError_t e = cudaGetDevice(&device);
-    if (e != cudaSuccess)
-        return (int)e;
-    cudaMemPool_t pool = nullptr;
-    int rc = ppx_scratch_pool(device, &pool);
-    if (rc != PPX_OK)
-        return rc;
-    cudaStream_t s = (cudaStream_t)stream;
-    unsigned char *hard = nullptr;
-    e = cudaMallocFromPoolAsync((void **)&hard, n, pool, s);
-    if (e != cudaSuccess)
-        return (int)e;
-    e = cudaMemsetAsync(hard, 0, n, s);
-    rc = e != cudaSuccess ? (int)e : dispatch(layout, OpIkStepLU{ch, q, Tt, q_out, Vs, hard}, n, ld, stream);
-    if (rc == PPX_OK)
-        rc = dispatch(layout, OpIkStepSvd<6>{ch, q, Tt, q_out, Vs, hard}, n, ld, stream);
-    const cudaError_t fe = cudaFreeAsync(hard, s);
-    return rc != PPX_OK ? rc : (int)fe;
+    if (NJ == 6 && g_ppx_square_lu.load(std::memory_order_relaxed) != 0)
+        return dispatch(layout, OpIkStep<NJ, false>{ch, q, Tt, q_out, Vs}, n, ld, stream);
+    return dispatch(layout, OpIkStep<NJ, true>{ch, q, Tt, q_out, Vs}, n, ld, stream);
 }
 
 // Launch of a persistent kernel with a work counter: as many CTAs as are resident at once; the counter lives for this
@@ -587,7 +499,7 @@ int ppx_cuda_batch_ik_newton_step(const double *screws, const double *home, int 
     case 3: return ik_step_n<3>(screws, home, q, Ttarget, q_out, Vs, n, layout, ld, stream);
     case 4: return ik_step_n<4>(screws, home, q, Ttarget, q_out, Vs, n, layout, ld, stream);
     case 5: return ik_step_n<5>(screws, home, q, Ttarget, q_out, Vs, n, layout, ld, stream);
-    case 6: return ik_step_6(screws, home, q, Ttarget, q_out, Vs, n, layout, ld, stream);
+    case 6: return ik_step_n<6>(screws, home, q, Ttarget, q_out, Vs, n, layout, ld, stream);
     }
     return PPX_ERR_BAD_SHAPE;
 }

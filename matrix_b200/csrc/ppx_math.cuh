@@ -1274,7 +1274,10 @@ static long g_ppx_svd_sweeps = 0;
 #ifndef PPX_SVD_PRECOND
 #define PPX_SVD_PRECOND 1 // single-precision preconditioning sweeps (jacobi_precondition_f32); 0: fp64 from the start
 #endif
-template <int M, int N, bool WANT_V, bool WANT_C = false>
+// PRECOND: run the single-precision preconditioning sweeps first.  It pays where V is wanted anyway (SVD, pinv,
+// rectangular linsolve<SVD>: +23-25 %) and for norm2 (+12 %); the row-orthogonalising square solve, which otherwise
+// accumulates no V at all, loses with it (IK step with the SVD solve forced: 1.84 against 2.13 G inst/s).
+template <int M, int N, bool WANT_V, bool WANT_C = false, bool PRECOND = (PPX_SVD_PRECOND != 0 && !WANT_C)>
 PPX_DEV void jacobi_svd_core(double (&A)[M * N], double (&V)[N * N], double (&w2)[N], double *carry = nullptr)
 {
     double a[N][M], v[N][N], nrm[N], cv[N];
@@ -1291,8 +1294,7 @@ PPX_DEV void jacobi_svd_core(double (&A)[M * N], double (&V)[N * N], double (&w2
         for (int i = 0; i < N; i++)
             v[j][i] = (i == j) ? 1.0 : 0.0;
     }
-#if PPX_SVD_PRECOND
-    if (N >= 3)
+    if (PRECOND && N >= 3)
     {
         // start the fp64 iteration from A V0, V = V0 (and the carried vector from V0^T carry)
         jacobi_precondition_f32<M, N>(a, v);
@@ -1330,7 +1332,6 @@ PPX_DEV void jacobi_svd_core(double (&A)[M * N], double (&V)[N * N], double (&w2
             for (int i = 0; i < M; i++)
                 a[j][i] = t[j][i];
     }
-#endif
     constexpr double TOL2 = 16.0 * M * EPS_DP * EPS_DP;
     constexpr int MAX_SWEEPS = 12;
     bool reversed = false;
@@ -1452,7 +1453,7 @@ PPX_DEV void jacobi_svd_solve(const double (&A)[M * N], const double (&V)[N * N]
 // same Jacobi machinery (columns of A^T) and carry b through the rotations.  With G = U^T A (orthogonal rows g_j of
 // norm w_j) and c = U^T b,  A^+ b = G^T diag(1/w^2) c = sum_j g_j c_j / w_j^2  over w_j > tsh -- the same truncation as
 // SVD::solve (linalg.hpp:886-913), 64 instead of 88 fp64 instructions per rotation.
-template <int N>
+template <int N, bool PRECOND = false>
 PPX_DEV void jacobi_rowsolve(const double (&A)[N * N], const double (&b)[N], double (&x)[N])
 {
     double At[N * N], dummy[N * N], w2[N], c[N];
@@ -1464,7 +1465,7 @@ PPX_DEV void jacobi_rowsolve(const double (&A)[N * N], const double (&b)[N], dou
         for (int j = 0; j < N; j++)
             At[j + r * N] = A[r + j * N];
     }
-    jacobi_svd_core<N, N, false, true>(At, dummy, w2, c);
+    jacobi_svd_core<N, N, false, true, PRECOND>(At, dummy, w2, c);
     double wmax2 = w2[0];
 #pragma unroll
     for (int j = 1; j < N; j++)
@@ -1493,29 +1494,11 @@ PPX_DEV void jacobi_rowsolve(const double (&A)[N * N], const double (&b)[N], dou
 // before truncation could matter; false for zero, inf and NaN pivots -- the row-orthogonalising Jacobi solve is run as
 // well and its result taken for those lanes.  The decision to run it is per warp, so well-conditioned batches never
 // execute it.  `allow_lu = false` forces the Jacobi path.
-// The Jacobi fallback as an out-of-line function (-DPPX_PINV_COLD=1).  Tried and measured on the IK Newton step: the
-// registers that are live across the call get spilled around it and the common path pays for that -- 8.7 G inst/s
-// against 10.0 G with the fallback inlined -- so it is off.
-#ifndef PPX_PINV_COLD
-#define PPX_PINV_COLD 0
-#endif
-template <int N>
-__device__ __noinline__ void jacobi_rowsolve_cold(const double *A, const double *b, double *x)
-{
-    double a[N * N], rhs[N], sol[N];
-#pragma unroll
-    for (int i = 0; i < N * N; i++)
-        a[i] = A[i];
-#pragma unroll
-    for (int i = 0; i < N; i++)
-        rhs[i] = b[i];
-    jacobi_rowsolve<N>(a, rhs, sol);
-#pragma unroll
-    for (int i = 0; i < N; i++)
-        x[i] = sol[i];
-}
-
-template <int N>
+// (Tried and dropped: the Jacobi fallback as a __noinline__ function, so that the common path would not share its
+// register allocation -- the registers live across the call get spilled around it and the common path pays: IK Newton
+// step 8.7 against 10.0 G inst/s.  A separate second-pass kernel over the instances the LU pass marks was measured too:
+// 7.9-8.3 G inst/s.  The fallback stays inline, behind a warp vote.)
+template <int N, bool PRECOND_FALLBACK = false>
 PPX_DEV void square_pinv_solve(const double (&A)[N * N], const double (&b)[N], double (&x)[N], bool allow_lu)
 {
     double rx[N];
@@ -1542,20 +1525,7 @@ PPX_DEV void square_pinv_solve(const double (&A)[N * N], const double (&b)[N], d
         }
     }
     double xs[N];
-#if PPX_PINV_COLD
-    {
-        double Ac[N * N], bc[N];
-#pragma unroll
-        for (int i = 0; i < N * N; i++)
-            Ac[i] = A[i];
-#pragma unroll
-        for (int i = 0; i < N; i++)
-            bc[i] = b[i];
-        jacobi_rowsolve_cold<N>(Ac, bc, xs);
-    }
-#else
-    jacobi_rowsolve<N>(A, b, xs);
-#endif
+    jacobi_rowsolve<N, PRECOND_FALLBACK>(A, b, xs);
 #pragma unroll
     for (int i = 0; i < N; i++)
         x[i] = easy ? rx[i] : xs[i];

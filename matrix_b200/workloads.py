@@ -190,12 +190,14 @@ class Se3ExpLog(Workload):
 class Se3ExpLog1M(Se3ExpLog):
     """config 1 at its stated size, 1M twists (96 MB per launch: it would sit in the 126 MB L2), over NBUF = 8 rotating
     buffer sets (768 MB touched per rotation) so that every launch streams from and to HBM.  A launch lasts ~17 us, the
-    scale of a launch from Python, so the rotation is captured once in a CUDA graph and step() replays it: one step =
-    NBUF launches over NBUF x 1M instances."""
+    scale of a launch from Python and of a kernel's ramp-up and tail, so the rotation is captured once in a CUDA graph
+    -- the 8 independent launches forked over LANES = 4 streams, so that one launch's tail overlaps the next one's
+    start -- and step() replays it: one step = NBUF launches over NBUF x 1M instances."""
     name = "se3_exp_log_1M"
-    kernel = "batch_kernel_pf<SOA, OpSe3ExpLog> x8 (CUDA graph over 8 rotating 1M-twist buffer sets)"
+    kernel = "batch_kernel_pf<SOA, OpSe3ExpLog> x8 (CUDA graph: 8 rotating 1M-twist buffer sets, 4 launches in flight)"
     n_default = 1 << 20
     NBUF = 8
+    LANES = 4
 
     def setup(self):
         self.bufs = []
@@ -206,10 +208,22 @@ class Se3ExpLog1M(Se3ExpLog):
         for xi, out in self.bufs:  # warm-up outside the capture: occupancy queries, attribute calls
             mb.se3_exp_log(xi, layout=mb.SOA, out=out)
         torch.cuda.synchronize()
+        side = [torch.cuda.Stream(device=self.device) for _ in range(self.LANES - 1)]
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            for xi, out in self.bufs:
-                mb.se3_exp_log(xi, layout=mb.SOA, out=out)
+            cur = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            for st in side:
+                st.wait_event(fork)
+            for b, (xi, out) in enumerate(self.bufs):
+                lane = b % self.LANES
+                with torch.cuda.stream(cur if lane == 0 else side[lane - 1]):
+                    mb.se3_exp_log(xi, layout=mb.SOA, out=out)  # launched on torch's current stream
+            for st in side:
+                join = torch.cuda.Event()
+                join.record(st)
+                cur.wait_event(join)
         self.launches_per_step = self.NBUF
         self.instances_per_step = self.NBUF * self.n
 

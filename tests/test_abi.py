@@ -161,3 +161,21 @@ def test_reference_arm_of_the_bench_runs_on_the_host():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d.get("gpu_launches", 0) == 0
+    # both arms describe the run with the same `config` (workload, instances per GPU and step, chain, N)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.config_for("ur5_fk_jacobian", 65536, 1)
+    from matrix_b200.workloads_meta import HEADLINE, META
+    assert META[HEADLINE]["n"] == 1 << 24  # the default step of the reference arm = the GPU arm's 16M instances
+
+
+def test_bench_tables_cover_every_baseline_config():
+    """every BASELINE.json config has a workload with its size, algorithmic bytes and a CPU leg (bench.py's `configs`)"""
+    import bench_cpu
+    from matrix_b200.workloads_meta import META
+    want = {"se3_exp_log_1M": (1 << 20, 96), "se3_exp_log": (1 << 26, 96), "ur5_fk_jacobian": (1 << 24, 464),
+            "linsolve_qr_4x3": (1 << 26, 153), "svd_6x6": (1 << 24, 912), "eig_sym_4": (1 << 24, 288),
+            "ik_newton_step": (1 << 25, 224)}
+    for name, (n, nbytes) in want.items():
+        assert META[name]["n"] == n and META[name]["bytes"] == nbytes and name in bench_cpu.CPU, name
+    assert 8 * META["ik_newton_step"]["n"] == 1 << 28  # config 5: 256M instances over 8 GPUs
