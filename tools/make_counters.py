@@ -30,7 +30,10 @@ for path in sys.argv[1:]:
                "dram_bytes_per_launch": s.get("dram_bytes"), "dram_gbs": s.get("dram_gbs"),
                "fp64_flops_per_instance": s.get("fp64_flops", 0) / n if s.get("fp64_flops") else None,
                "fp64_instr_per_instance": (s.get("dfma", 0) + s.get("dadd", 0) + s.get("dmul", 0)) / n,
+               "warp_instr_per_instance": s.get("inst_executed", 0) * 32 / n,  # one instance per thread
                "fp64_pipe_pct": s.get("fp64_pipe_pct"), "issue_active_pct": s.get("issue_active_pct"),
+               "pipe_fma_pct": s.get("pipe_fma_pct"), "pipe_alu_pct": s.get("pipe_alu_pct"),
+               "pipe_xu_pct": s.get("pipe_xu_pct"), "eligible_warps_per_cycle": s.get("eligible_warps"),
                "registers": s.get("regs"), "warps_active_pct": s.get("warps_active_pct")}
 json.dump(out, open(os.path.join(ROOT, "profiles", "counters.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))

@@ -32,6 +32,9 @@ KEYS = {
     "grid": ("launch__grid_size", 1.0),
     "block": ("launch__block_size", 1.0),
     "eligible_warps": ("smsp__warps_eligible.avg.per_cycle_active", 1.0),
+    "pipe_fma_pct": ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", 1.0),
+    "pipe_alu_pct": ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", 1.0),
+    "pipe_xu_pct": ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", 1.0),
 }
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3,
         "Ghz": 1e3, "Mhz": 1.0, "cycle/nsecond": 1e3, "cycle/usecond": 1.0}
