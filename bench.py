@@ -448,8 +448,10 @@ def multi_device_e2e(cls, n_per_gpu, n_all, world, steps, device, host, Arena):
     import statistics as st
     import torch
     t_pin = time.perf_counter()
-    big = Arena(n_all * cls.bytes_per_instance() + (64 << 20))
+    probe_bytes = world * (256 << 20)  # scratch of the copy probes and the tuner: they overwrite what they are given
+    big = Arena(n_all * cls.bytes_per_instance() + (64 << 20) + probe_bytes)
     t_pin = time.perf_counter() - t_pin
+    scratch = big.take((probe_bytes,), "uint8")
     # the inputs of all shards: regenerated shard by shard on this device (counter-based generator), copied to the host
     hq, w, first = None, None, 0
     while first < n_all:
@@ -484,17 +486,19 @@ def multi_device_e2e(cls, n_per_gpu, n_all, world, steps, device, host, Arena):
     direction = "d2h" if share > 2 / 3 else ("h2d" if share < 1 / 3 else "both")
     try:
         dt_all, per_all = timed(everyone)
-        rates_all = {d: host.copy_probe(big.buf, d, 1.0) for d in sorted({"d2h", direction})}
+        rates_all = {d: host.copy_probe(scratch, d, 1.0) for d in sorted({"d2h", direction})}
         # let the library pick the devices whose links carry the most together (ppx_cuda_host_tune_devices)
         t_tune = time.perf_counter()
-        chosen, tuned_gbs = host.tune_devices(everyone, big.buf, direction, 0.15)
+        chosen, tuned_gbs = host.tune_devices(everyone, scratch, direction, 0.15)
         t_tune = time.perf_counter() - t_tune
         if chosen != everyone:
             dt_sel, per_sel = timed(chosen)
-            rates_sel = host.copy_probe(big.buf, direction, 1.0)
+            rates_sel = host.copy_probe(scratch, direction, 1.0)
         else:
             dt_sel, per_sel, rates_sel = dt_all, per_all, rates_all[direction]
-        probe = float(h_out[0].reshape(n_all, -1)[-1, -1])
+        probe = float(h_out[0].reshape(n_all, -1)[-1, -1])  # a value of the last instance's result: it arrived
+        if cls.name.startswith("ur5_fk") and probe != 1.0:
+            raise RuntimeError(f"end-to-end result not written: T[-1][15] = {probe}")
     finally:
         host.set_devices(None)
     use_sel = dt_sel < dt_all

@@ -1571,6 +1571,18 @@ PPX_DEV void jacobi_eig_sym(const double (&S)[N * N], bool sorted, double (&d)[N
     constexpr int MAX_SWEEPS = 12;
     for (int sweep = 0; sweep < MAX_SWEEPS; sweep++)
     {
+        // Done when no off-diagonal of any lane is above the threshold.  Testing that directly costs N(N-1)/2 multiplies
+        // and compares; finding it out by running a sweep in which no rotation acts costs that sweep's N(N-1)/2 rotation
+        // derivations (two reciprocal square roots and a reciprocal each) -- it is the same decision, so the results are
+        // bit-identical, and the last sweep of every matrix is saved
+        bool big = false;
+#pragma unroll
+        for (int p = 0; p < N; p++)
+#pragma unroll
+            for (int q = p + 1; q < N; q++)
+                big |= a[sym_ix(p, q, N)] * a[sym_ix(p, q, N)] > thr2;
+        if (!__any_sync(0xffffffffu, big))
+            break;
         bool rotated = false;
 #pragma unroll
         for (int r = 0; r < TT::ROUNDS; r++)
