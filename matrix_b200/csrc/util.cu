@@ -164,7 +164,7 @@ int grid_for(size_t n, int block)
 extern "C"
 {
 
-const char *ppx_cuda_version(void) { return "ppx-b200 0.1 (sm_100a, fp64, reference ppx v1.2)"; }
+const char *ppx_cuda_version(void) { return "ppx-b200 0.2 (sm_100a, fp64, reference ppx v1.2)"; }
 
 const char *ppx_cuda_error_string(int code)
 {

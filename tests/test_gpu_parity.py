@@ -1070,6 +1070,23 @@ def test_host_face_device_list(mb):
     host.set_devices(None)
 
 
+def test_device_list_from_the_environment(mb):
+    """PPX_CUDA_DEVICES is read once, at the first host-face call of a process: "all", a list, or garbage (ignored)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import numpy as np; from matrix_b200 import host; "
+            "x = host.se3_exp_log(np.full((4, 6), 0.25)); print(host.get_devices(), float(x[0, 0]))")
+    ndev = torch.cuda.device_count()
+    for value, want in (("all", list(range(ndev))), ("0", [0]), ("0,0", []), ("7x", []), ("", [])):
+        env = dict(os.environ, PPX_CUDA_DEVICES=value)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-1500:]
+        got, val = r.stdout.strip().rsplit("] ", 1)
+        assert eval(got + "]") == want, (value, r.stdout)
+        assert abs(float(val) - 0.25) < 1e-12
+
+
 def test_two_device_host_call_is_bitwise_the_one_device_result(mb, port):
     """one host call spread over two GPUs (one worker thread per device, chunks from a shared queue) gives
     bit for bit what one GPU gives -- and both match the oracle."""
