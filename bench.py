@@ -297,10 +297,16 @@ def main():
         every rank runs its own shard at once, time = max over ranks"""
         nonlocal arena
         if arena is None:
-            arena = Arena(ARENA_BYTES)
+            try:
+                import psutil
+                avail = psutil.virtual_memory().available
+            except Exception:
+                avail = 64 << 30
+            # every rank page-locks its own arena: leave the host 60 % of what is free
+            arena = Arena(max(min(ARENA_BYTES, int(0.4 * avail / world)), 64 << 20))
         arena.reset()
         n_e2e = n
-        while n_e2e * cls.bytes_per_instance() + (1 << 20) > ARENA_BYTES and n_e2e > 1024:
+        while n_e2e * cls.bytes_per_instance() + (1 << 20) > arena.buf.size and n_e2e > 1024:
             n_e2e //= 2  # e.g. svd_6x6: 912 B per instance, 8M instances per call instead of 16M
         h2d, d2h = w.host_setup(n_e2e, arena)
         w.host_step()  # warm-up (stream-ordered pool growth)
@@ -399,7 +405,7 @@ def main():
     elif e2e is not None and rank == 0:
         # the ceiling of the one-device host path: what this device's link carries when it only copies
         arena.reset()
-        buf = arena.take((1 << 30,), "uint8")
+        buf = arena.take((min(1 << 30, arena.buf.size - (1 << 20)),), "uint8")
         rates = {d: host.copy_probe(buf, d, 0.5)[0] for d in ("h2d", "d2h", "both")}
         e2e["ceiling"] = {"probe": "ppx_cuda_host_copy_probe: the same pinned arena, 48 MiB pieces, no kernels, 0.5 s each",
                           "h2d_gbs": rates["h2d"], "d2h_gbs": rates["d2h"], "both_gbs": rates["both"],
