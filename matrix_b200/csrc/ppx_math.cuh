@@ -1128,19 +1128,25 @@ PPX_DEV F2 f2_set(float x, float y)
 // (fp32 range: the copy is scaled by an exact power of two so that the largest entry is in [1, 2); entries 2^-126
 // below it flush to zero, which a preconditioner may ignore.)
 template <int MH, int NH>
-PPX_DEV void f32_rotate_pair(F2 (&ap)[MH], F2 (&aq)[MH], F2 (&vp)[NH], F2 (&vq)[NH], float &np_, float &nq_, float tol2)
+PPX_DEV void f32_rotate_pair(F2 (&ap)[MH], F2 (&aq)[MH], F2 (&vp)[NH], F2 (&vq)[NH], float &np_, float &nq_)
 {
     F2 acc = f2_set(0.0f, 0.0f);
 #pragma unroll
     for (int i = 0; i < MH; i++)
         acc = f2_fma(ap[i], aq[i], acc);
     const float ga = acc.x + acc.y;
-    const bool act = ga * ga > tol2 * (np_ * nq_);
-    float c, s, t;
-    jacobi_cst<float>(np_, nq_, ga, c, s, t);
-    c = act ? c : 1.0f;
-    s = act ? s : 0.0f;
-    t = act ? t : 0.0f;
+    // the rotation that annihilates ga (jacobi_cst), without the "is it worth rotating" test of the fp64 iteration:
+    // the sweep count is fixed here, and a negligible ga gives c = 1, s = t = 0 by itself once the radicand cannot be
+    // zero (1e-37 is below the square of anything the scaled copy can hold next to an entry in [1, 2))
+    const float d = nq_ - np_;
+    const float g2 = ga + ga;
+    const float gg = g2 * g2;
+    const float r = fmaf(d, d, gg) + 1e-37f;
+    const float h = r * rsqrt_nr(r);
+    const float u = fabsf(d) + h;
+    const float w = rsqrt_nr(fmaf(u, u, gg));
+    const float sg = d >= 0.0f ? g2 : -g2;
+    const float c = u * w, s = sg * w, t = sg * rcp_nr(u);
     const float n0 = fmaf(-t, ga, np_), n1 = fmaf(t, ga, nq_);
     np_ = n1; // the rotated columns swap positions
     nq_ = n0;
@@ -1192,7 +1198,6 @@ PPX_DEV void jacobi_precondition_f32(const double (&a64)[N][M], double (&v0)[N][
         for (int i = 0; i < NH; i++)
             v[j][i] = f2_set(2 * i == j ? 1.0f : 0.0f, 2 * i + 1 == j ? 1.0f : 0.0f);
     }
-    constexpr float TOL2 = 16.0f * M * 1.4210855e-14f; // (4 sqrt(M) eps_f)^2, eps_f = 2^-23
 #pragma unroll 1
     for (int sweep = 0; sweep < SWEEPS; sweep++)
     {
@@ -1210,16 +1215,16 @@ PPX_DEV void jacobi_precondition_f32(const double (&a64)[N][M], double (&v0)[N][
         {
 #pragma unroll
             for (int k = 0; k + 1 < N; k += 2)
-                f32_rotate_pair<MH, NH>(a[k], a[k + 1], v[k], v[k + 1], nrm[k], nrm[k + 1], TOL2);
+                f32_rotate_pair<MH, NH>(a[k], a[k + 1], v[k], v[k + 1], nrm[k], nrm[k + 1]);
 #pragma unroll
             for (int k = 1; k + 1 < N; k += 2)
-                f32_rotate_pair<MH, NH>(a[k], a[k + 1], v[k], v[k + 1], nrm[k], nrm[k + 1], TOL2);
+                f32_rotate_pair<MH, NH>(a[k], a[k + 1], v[k], v[k + 1], nrm[k], nrm[k + 1]);
         }
         if (N & 1)
         {
 #pragma unroll
             for (int k = 0; k + 1 < N; k += 2)
-                f32_rotate_pair<MH, NH>(a[k], a[k + 1], v[k], v[k + 1], nrm[k], nrm[k + 1], TOL2);
+                f32_rotate_pair<MH, NH>(a[k], a[k + 1], v[k], v[k + 1], nrm[k], nrm[k + 1]);
         }
     }
     // V0 in fp64, orthonormalised by modified Gram-Schmidt (an even number of sweeps left the columns in order)
