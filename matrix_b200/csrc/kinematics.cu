@@ -44,7 +44,10 @@ struct OpFkJacobian
 #ifndef PPX_FK_MINB
 #define PPX_FK_MINB 3
 #endif
-    static constexpr int BLOCK = 128, MINB = PPX_FK_MINB, MAXW = (WANT_J ? 6 * NJ : 16) > 16 ? (WANT_J ? 6 * NJ : 16) : 16;
+#ifndef PPX_FK_BLOCK
+#define PPX_FK_BLOCK 128
+#endif
+    static constexpr int BLOCK = PPX_FK_BLOCK, MINB = PPX_FK_MINB, MAXW = (WANT_J ? 6 * NJ : 16) > 16 ? (WANT_J ? 6 * NJ : 16) : 16;
     ChainConst<NJ> ch;
     const double *q;
     double *T;

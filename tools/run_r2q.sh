@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2q_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2q_pytest.log; tail -3 gpurun_out/r2q_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2q_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/r2q_smoke.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2q_bench_n1.json 2> gpurun_out/r2q_bench_n1.err; echo "bench rc=$?"
+python tools/design_tables.py gpurun_out/r2q_bench_n1.json | cut -c1-200
+timeout 600 python bench.py --all-ops > gpurun_out/r2q_all_ops.json 2> gpurun_out/r2q_all_ops.err; echo "allops rc=$?"
+timeout 600 python bench.py --all-ops --layout aos > gpurun_out/r2q_all_ops_aos.json 2>> gpurun_out/r2q_all_ops.err; echo "allops aos rc=$?"
