@@ -7,6 +7,7 @@
 // only NJ sincos, NJ-1 rigid products shared between the pose and the Jacobian columns, and NJ-1
 // structured adjoint applications: no division, no square root, no 4x4 matrix powers.
 #include <cmath>
+#include <cstdlib>
 
 #include "ppx_launch.cuh"
 
@@ -100,13 +101,13 @@ __device__ __forceinline__ typename std::enable_if<NJ != 6>::type svd_solve_disp
 }
 
 // Vs = Ad(T(q)) log(T(q)^-1 Tt),  dq = pinv(Js(q)) Vs  (test/lie_test.cpp:104-110)
-template <int NJ, bool PRECOND = true>
+template <int NJ, bool PRECOND = true, class Kinds = RuntimeKinds>
 __device__ __forceinline__ void ik_newton_update(const ChainConst<NJ> &ch, const Rigid &target, double (&q)[NJ],
                                                  double (&vs)[6], bool allow_lu)
 {
     Rigid t, ti, x;
     double js[6 * NJ];
-    poe_fk_jacobian<NJ, true, true>(ch, q, t, [&](int col, const double(&v)[6]) {
+    poe_fk_jacobian<NJ, true, true, Kinds>(ch, q, t, [&](int col, const double(&v)[6]) {
 #pragma unroll
         for (int k = 0; k < 6; k++)
             js[6 * col + k] = v[k];
@@ -137,7 +138,13 @@ __device__ __forceinline__ void ik_newton_update(const ChainConst<NJ> &ch, const
 #ifndef PPX_IK_MINB
 #define PPX_IK_MINB 3
 #endif
-template <int NJ, bool SVD_ONLY>
+// joint-axis patterns with kernels of their own (FixedKinds): the Universal-Robots family and its many look-alikes
+// (z y y y z y: UR3/5/10/16/20, the reference's own fixture), and the classic 6R arm with a spherical wrist in its
+// home pose (z y y x y x: PUMA, ABB IRB, KUKA KR, Fanuc, ...).  Any other chain runs the RuntimeKinds kernels.
+using KindsUR = FixedKinds<3, 2, 2, 2, 3, 2>;
+using KindsWrist = FixedKinds<3, 2, 2, 1, 2, 1>;
+
+template <int NJ, bool SVD_ONLY, class Kinds = RuntimeKinds>
 struct OpIkStep
 {
     static constexpr int BLOCK = 128, MINB = SVD_ONLY ? 2 : PPX_IK_MINB, MAXW = 16;
@@ -177,7 +184,7 @@ struct OpIkStep
         double vs[6];
         Rigid target;
         rigid_from_record(m, target);
-        ik_newton_update<NJ, !SVD_ONLY>(ch, target, qi, vs, !SVD_ONLY);
+        ik_newton_update<NJ, !SVD_ONLY, Kinds>(ch, target, qi, vs, !SVD_ONLY);
         io.store(q_out, qi);
         if (Vs != nullptr)
             io.store(Vs, vs);
@@ -233,7 +240,7 @@ struct IkSolveArgs
     bool allow_lu;
 };
 
-template <int LAYOUT>
+template <int LAYOUT, class Kinds>
 __global__ void __launch_bounds__(128, PPX_IK_MINB)
     ik_solve_kernel(const __grid_constant__ IkSolveArgs a, size_t n, size_t ld, unsigned long long *next)
 {
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(128, PPX_IK_MINB)
 #pragma unroll
         for (int i = 0; i < NJ; i++)
             qn[i] = qi[i];
-        ik_newton_update<NJ>(a.ch, target, qn, vs, a.allow_lu);
+        ik_newton_update<NJ, true, Kinds>(a.ch, target, qn, vs, a.allow_lu);
         if (busy && !finished)
         {
 #pragma unroll
@@ -399,15 +406,51 @@ int fk_jacobian_n(const double *screws, const double *home, const double *q, dou
     return dispatch(layout, OpFkJacobian<NJ, false, true>{ch, q, nullptr, Js}, n, ld, stream);
 }
 
+// PPX_IK_PATTERNS=0 in the environment keeps every chain on the RuntimeKinds kernels (tests compare the two)
+inline bool ik_patterns_enabled()
+{
+    const char *e = std::getenv("PPX_IK_PATTERNS");
+    return !(e && e[0] == '0');
+}
+
+template <int NJ, class Kinds>
+int ik_step_launch(const ChainConst<NJ> &ch, bool lu, const double *q, const double *Tt, double *q_out, double *Vs,
+                   size_t n, int layout, size_t ld, void *stream)
+{
+    if (lu)
+        return dispatch(layout, OpIkStep<NJ, false, Kinds>{ch, q, Tt, q_out, Vs}, n, ld, stream);
+    return dispatch(layout, OpIkStep<NJ, true, Kinds>{ch, q, Tt, q_out, Vs}, n, ld, stream);
+}
+template <int NJ>
+typename std::enable_if<NJ == 6, int>::type ik_step_dispatch(const ChainConst<NJ> &ch, bool lu, const double *q,
+                                                             const double *Tt, double *q_out, double *Vs, size_t n,
+                                                             int layout, size_t ld, void *stream)
+{
+    if (ik_patterns_enabled())
+    {
+        if (KindsUR::matches(ch))
+            return ik_step_launch<NJ, KindsUR>(ch, lu, q, Tt, q_out, Vs, n, layout, ld, stream);
+        if (KindsWrist::matches(ch))
+            return ik_step_launch<NJ, KindsWrist>(ch, lu, q, Tt, q_out, Vs, n, layout, ld, stream);
+    }
+    return ik_step_launch<NJ, RuntimeKinds>(ch, lu, q, Tt, q_out, Vs, n, layout, ld, stream);
+}
+template <int NJ>
+typename std::enable_if<NJ != 6, int>::type ik_step_dispatch(const ChainConst<NJ> &ch, bool lu, const double *q,
+                                                             const double *Tt, double *q_out, double *Vs, size_t n,
+                                                             int layout, size_t ld, void *stream)
+{
+    return ik_step_launch<NJ, RuntimeKinds>(ch, lu, q, Tt, q_out, Vs, n, layout, ld, stream);
+}
+
 template <int NJ>
 int ik_step_n(const double *screws, const double *home, const double *q, const double *Tt, double *q_out,
               double *Vs, size_t n, int layout, size_t ld, void *stream)
 {
     ChainConst<NJ> ch;
     fold_chain<NJ>(screws, home, ch);
-    if (NJ == 6 && g_ppx_square_lu.load(std::memory_order_relaxed) != 0)
-        return dispatch(layout, OpIkStep<NJ, false>{ch, q, Tt, q_out, Vs}, n, ld, stream);
-    return dispatch(layout, OpIkStep<NJ, true>{ch, q, Tt, q_out, Vs}, n, ld, stream);
+    const bool lu = NJ == 6 && g_ppx_square_lu.load(std::memory_order_relaxed) != 0;
+    return ik_step_dispatch<NJ>(ch, lu, q, Tt, q_out, Vs, n, layout, ld, stream);
 }
 
 // Launch of a persistent kernel with a work counter: as many CTAs as are resident at once; the counter lives for this
@@ -526,8 +569,15 @@ int ppx_cuda_batch_ik_solve(const double *screws, const double *home, int njoint
     fold_chain<6>(screws, home, a.ch);
     a.q0 = q0, a.Tt = Ttarget, a.q_out = q_out, a.iters = iters, a.status = status, a.max_iter = max_iter;
     a.allow_lu = g_ppx_square_lu.load(std::memory_order_relaxed) != 0;
-    return layout == PPX_LAYOUT_AOS ? launch_persistent<ik_solve_kernel<LAYOUT_AOS>>(128, 0, a, n, ld, stream)
-                                    : launch_persistent<ik_solve_kernel<LAYOUT_SOA>>(128, 0, a, n, ld, stream);
+    const bool aos = layout == PPX_LAYOUT_AOS;
+    if (ik_patterns_enabled() && KindsUR::matches(a.ch))
+        return aos ? launch_persistent<ik_solve_kernel<LAYOUT_AOS, KindsUR>>(128, 0, a, n, ld, stream)
+                   : launch_persistent<ik_solve_kernel<LAYOUT_SOA, KindsUR>>(128, 0, a, n, ld, stream);
+    if (ik_patterns_enabled() && KindsWrist::matches(a.ch))
+        return aos ? launch_persistent<ik_solve_kernel<LAYOUT_AOS, KindsWrist>>(128, 0, a, n, ld, stream)
+                   : launch_persistent<ik_solve_kernel<LAYOUT_SOA, KindsWrist>>(128, 0, a, n, ld, stream);
+    return aos ? launch_persistent<ik_solve_kernel<LAYOUT_AOS, RuntimeKinds>>(128, 0, a, n, ld, stream)
+               : launch_persistent<ik_solve_kernel<LAYOUT_SOA, RuntimeKinds>>(128, 0, a, n, ld, stream);
 }
 
 int ppx_cuda_batch_ik_codo(const double *screws, const double *home, int njoints, const double *lo, const double *hi,

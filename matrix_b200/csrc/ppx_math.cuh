@@ -614,14 +614,51 @@ PPX_DEV void poe_joint(const JointConst &j, double q, Rigid &P, int i, bool firs
     }
 }
 
+// Where the kinds of a chain's joints come from.  RuntimeKinds reads them from the per-call constants: one uniform
+// 4-way branch per joint, any chain.  FixedKinds<k0, k1, ...> makes them compile-time constants: the branch folds away
+// and only the variant each joint needs is compiled -- used for the joint-axis patterns of the common 6R arm
+// families (kinematics.cu: KindsUR, KindsWrist), where the branches and the 4x larger code cost the latency-bound IK
+// kernels 8-17 % (profiles/r2r_ab.log); the memory-bound FK kernel is indifferent and always uses RuntimeKinds.
+struct RuntimeKinds
+{
+    template <int NJ>
+    PPX_DEV static int get(const ChainConst<NJ> &ch, int i)
+    {
+        return ch.joint[i].kind;
+    }
+};
+template <int... K>
+struct FixedKinds
+{
+    static constexpr int N = sizeof...(K);
+    template <int NJ>
+    PPX_DEV static int get(const ChainConst<NJ> &, int i)
+    {
+        constexpr int table[sizeof...(K) + 1] = {K..., 0};
+        return table[i < N ? i : N];
+    }
+    // host side: does this chain have exactly these kinds?
+    template <int NJ>
+    static bool matches(const ChainConst<NJ> &ch)
+    {
+        constexpr int table[sizeof...(K) + 1] = {K..., 0};
+        if (NJ != N)
+            return false;
+        for (int i = 0; i < NJ; i++)
+            if (ch.joint[i].kind != table[i])
+                return false;
+        return true;
+    }
+};
+
 // forwardSpace + jacobiSpace in one pass (demo/robotics.hpp:83-106).  The prefix products
 // P_i = e^{S_0 q_0} ... e^{S_{i-1} q_{i-1}} are shared: column i of Js is Ad(P_i) S_i and the pose is
 // P_N M.  (The reference associates forwardSpace right-to-left; sharing the prefixes changes the
 // association, a 1e-16 effect.)  Each Jacobian column is handed to `emit(i, col)` as soon as it exists,
-// so a caller that streams columns out never holds the 6 x NJ matrix in registers.  The kind of every joint is a
-// per-call constant (constant bank), so the switch below is a uniform branch: no divergence, and only the variant a
-// chain uses is ever fetched.
-template <int NJ, bool WANT_T, bool WANT_J, class Emit>
+// so a caller that streams columns out never holds the 6 x NJ matrix in registers.  With RuntimeKinds the kind of every
+// joint is a per-call constant (constant bank), so the switch below is a uniform branch: no divergence, and only the
+// variant a chain uses is ever fetched; with FixedKinds it is resolved at compile time.
+template <int NJ, bool WANT_T, bool WANT_J, class Kinds = RuntimeKinds, class Emit>
 PPX_DEV void poe_fk_jacobian(const ChainConst<NJ> &ch, const double (&q)[NJ], Rigid &T, Emit &&emit)
 {
     Rigid P;
@@ -629,7 +666,7 @@ PPX_DEV void poe_fk_jacobian(const ChainConst<NJ> &ch, const double (&q)[NJ], Ri
     for (int i = 0; i < NJ; i++)
     {
         const bool first = i == 0, advance = WANT_T || i < NJ - 1;
-        switch (ch.joint[i].kind)
+        switch (Kinds::get(ch, i))
         {
         case 1: poe_joint<1>(ch.joint[i], q[i], P, i, first, WANT_J, advance, emit); break;
         case 2: poe_joint<2>(ch.joint[i], q[i], P, i, first, WANT_J, advance, emit); break;

@@ -255,6 +255,63 @@ def test_mixed_axis_aligned_and_general_chain(mb, cpu_ref):
     assert ok.mean() > 0.9 and np.all(err[ok] <= REL * np.maximum(1.0, kappa[ok]))
 
 
+WRIST_CHAIN = np.array([  # a 6R arm with a spherical wrist in its home pose: axes z y y x y x (PUMA / ABB / KUKA style)
+    [0.0, 0.0, 1.0, 0.0, 0.0, 0.0],
+    [0.0, 1.0, 0.0, -0.40, 0.0, 0.03],
+    [0.0, 1.0, 0.0, -0.40, 0.0, 0.48],
+    [-1.0, 0.0, 0.0, 0.0, -0.44, 0.0],
+    [0.0, 1.0, 0.0, -0.44, 0.0, 0.90],
+    [1.0, 0.0, 0.0, 0.0, 0.44, 0.0],
+])
+WRIST_HOME = np.array([0.0, 0.0, -1.0, 0.0, 0.0, 1.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.44, 1.0])
+
+
+@pytest.mark.parametrize("chain", ["ur5", "wrist"])
+def test_pattern_kernels_match_the_generic_ones_and_the_oracle(mb, cpu_ref, chain):
+    """Chains whose joint axes follow a precompiled pattern (FixedKinds: z y y y z y, z y y x y x) run IK kernels in
+    which the per-joint branch is resolved at compile time; PPX_IK_PATTERNS=0 keeps them on the generic kernels.  Same
+    arithmetic, so the two must agree bit for bit -- Newton step in both solve modes, and the whole Newton loop -- and
+    both with the oracle."""
+    from matrix_b200 import _lib
+    S, M = (synth.UR5_SCREWS, synth.UR5_HOME) if chain == "ur5" else (WRIST_CHAIN, WRIST_HOME)
+    n = 50_003
+    q = synth.joint_angles(n, seed=0xC4B1)
+    Tt = cpu_ref.poe_fk_jacobian(S, M, q + synth.ik_offsets(n), want_Js=False)[0]
+    kin = mb.Kinematics(S, M)
+    out = {}
+    old = os.environ.get("PPX_IK_PATTERNS")
+    try:
+        for mode in ("1", "0"):
+            os.environ["PPX_IK_PATTERNS"] = mode
+            res = []
+            for lu in (True, False):
+                _lib.set_square_solve_lu(lu)
+                for layout in LAYOUTS:
+                    res.append(run(mb, kin.ik_newton_step, layout, q, Tt, want_Vs=True))
+            _lib.set_square_solve_lu(True)
+            qs, it, st = kin.inverseSpaceNewton(dev(Tt), dev(q), 20)
+            res.append((qs.cpu().numpy(), it.cpu().numpy(), st.cpu().numpy()))
+            out[mode] = res
+    finally:
+        _lib.set_square_solve_lu(True)
+        if old is None:
+            os.environ.pop("PPX_IK_PATTERNS", None)
+        else:
+            os.environ["PPX_IK_PATTERNS"] = old
+    for a, b in zip(out["1"], out["0"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    rq, rV = cpu_ref.ik_newton_step(S, M, q, Tt)
+    qo, Vs = out["1"][0]
+    assert rel_err(Vs, rV).max() < REL
+    Js = cpu_ref.poe_fk_jacobian(S, M, q, want_T=False)[1]
+    sv = np.linalg.svd(Js.reshape(n, 6, 6), compute_uv=False)
+    kappa = sv[:, 0] / sv[:, -1]
+    err = np.abs((qo - q) - (rq - q)).max(axis=1) / np.maximum(np.abs(rq - q).max(axis=1), 1e-300)
+    ok = kappa < 1e6
+    assert ok.mean() > 0.9 and np.all(err[ok] <= REL * np.maximum(1.0, kappa[ok]))
+
+
 def test_golden_ur5(mb, golden):
     g = golden["ur5"]
     kin = mb.Kinematics(np.array(g["screws"], dtype=float), np.array(g["home"]))
