@@ -325,7 +325,7 @@ struct IkCodoArgs
     int8_t *status;
 };
 
-template <int LAYOUT>
+template <int LAYOUT, class Kinds>
 __global__ void __launch_bounds__(PPX_CODO_BLOCK, PPX_CODO_MINB)
     ik_codo_kernel(const __grid_constant__ IkCodoArgs a, size_t n, size_t ld, unsigned long long *next)
 {
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(PPX_CODO_BLOCK, PPX_CODO_MINB)
         if (busy && !finished)
         {
             double fp[6];
-            codo_eval<6>(a.ch, poseI, st.probe, fp, codo_jac_probe(st));
+            codo_eval<6, Kinds>(a.ch, poseI, st.probe, fp, codo_jac_probe(st));
             finished = codo_advance(active, a.lo, a.hi, st, fp);
         }
         if (busy && finished)
@@ -601,8 +601,15 @@ int ppx_cuda_batch_ik_codo(const double *screws, const double *home, int njoints
         a.hi[i] = hi[i];
     }
     a.Tt = Ttarget, a.init = init, a.q_out = q_out, a.x_raw = x_raw, a.fnorm = fnorm, a.status = status;
-    return layout == PPX_LAYOUT_AOS ? launch_persistent<ik_codo_kernel<LAYOUT_AOS>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream)
-                                    : launch_persistent<ik_codo_kernel<LAYOUT_SOA>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream);
+    const bool aos = layout == PPX_LAYOUT_AOS;
+    if (ik_patterns_enabled() && KindsUR::matches(a.ch))
+        return aos ? launch_persistent<ik_codo_kernel<LAYOUT_AOS, KindsUR>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream)
+                   : launch_persistent<ik_codo_kernel<LAYOUT_SOA, KindsUR>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream);
+    if (ik_patterns_enabled() && KindsWrist::matches(a.ch))
+        return aos ? launch_persistent<ik_codo_kernel<LAYOUT_AOS, KindsWrist>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream)
+                   : launch_persistent<ik_codo_kernel<LAYOUT_SOA, KindsWrist>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream);
+    return aos ? launch_persistent<ik_codo_kernel<LAYOUT_AOS, RuntimeKinds>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream)
+               : launch_persistent<ik_codo_kernel<LAYOUT_SOA, RuntimeKinds>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream);
 }
 
 } // extern "C"
