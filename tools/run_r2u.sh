@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2u_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2u_pytest.log; tail -3 gpurun_out/r2u_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2u_bench_n1.json 2> gpurun_out/r2u_bench_n1.err; echo "bench rc=$?"
+python tools/design_tables.py gpurun_out/r2u_bench_n1.json | cut -c1-200
+timeout 600 python bench.py --all-ops > gpurun_out/r2u_all_ops.json 2> gpurun_out/r2u_all_ops.err; echo "allops rc=$?"
+timeout 600 python bench.py --all-ops --layout aos > gpurun_out/r2u_all_ops_aos.json 2>> gpurun_out/r2u_all_ops.err; echo "allops aos rc=$?"
+bash tools/profile_all.sh r2u 2>&1 | tail -10
+rm -f gpurun_out/prof_r2u_*.ncu-rep
