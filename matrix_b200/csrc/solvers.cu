@@ -74,7 +74,7 @@ struct OpSVD
             // a slow-path call); exactly zero columns (rank deficiency) stay exactly zero
             const bool pos = w2[j] >= DBL_MIN; // (a denormal squared norm, sigma < 1.5e-154 of the largest entry, counts as 0)
             const double rs = rsqrt_nr(pos ? w2[j] : 1.0);
-            const double ws = pos ? w2[j] * rs : 0.0;
+            const double ws = pos ? w2[j] * rs : (w2[j] < DBL_MIN ? 0.0 : w2[j]); // NaN in, NaN out
             sv[j] = ws;
             if (WANT_U)
             {

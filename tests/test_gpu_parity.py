@@ -488,6 +488,27 @@ def test_svd_rank_deficient_edge_cases(mb, fixtures, golden):
             assert abs(w.max() - case["norm2"]) < golden["matrix_norm2"]["tol"]
 
 
+def test_svd_with_nan_and_inf_instances_terminates_and_spares_the_others(mb, port):
+    """NaN / inf matrices mixed into a batch: the sweeps end by warp vote and the single-precision preconditioner runs
+    a fixed number of sweeps, so such a lane can neither hang its warp nor disturb the 31 ordinary matrices next to it"""
+    n = 4099
+    A = synth.dense(n, 6, 6, seed=0xBAD)
+    bad = np.arange(5, n, 37)
+    A[bad[0::3], 7] = np.nan
+    A[bad[1::3], 0] = np.inf
+    A[bad[2::3]] = np.nan
+    good = np.ones(n, dtype=bool)
+    good[bad] = False
+    for layout in LAYOUTS:
+        U, w, V = run(mb, lambda a_, layout: mb.svdcmp(6, 6, a_, layout=layout), layout, A)
+        _, rw, _ = port.svd(6, 6, A[good])
+        assert np.abs(np.sort(w[good], axis=1) - np.sort(rw, axis=1)).max() < 1e-12 * rw.max()
+        rec = np.einsum("nij,nj,nkj->nik", U[good].reshape(-1, 6, 6).transpose(0, 2, 1), w[good],
+                        V[good].reshape(-1, 6, 6).transpose(0, 2, 1))
+        assert np.abs(rec - A[good].reshape(-1, 6, 6).transpose(0, 2, 1)).max() < 1e-13
+        assert not np.isfinite(w[bad]).all(axis=1).any()  # the poisoned instances do not pretend to have an answer
+
+
 @pytest.mark.parametrize("layout", LAYOUTS)
 def test_linsolve_svd_6x6(mb, port, layout):
     n = 1 << 14
