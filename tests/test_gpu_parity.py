@@ -509,6 +509,44 @@ def test_svd_with_nan_and_inf_instances_terminates_and_spares_the_others(mb, por
         assert not np.isfinite(w[bad]).all(axis=1).any()  # the poisoned instances do not pretend to have an answer
 
 
+@pytest.mark.timeout(120)
+def test_nan_inputs_end_every_iterative_kernel(mb, port):
+    """a few NaN instances in a batch: every data-dependent loop (Jacobi sweeps by warp vote, the persistent Newton
+    loop and the trust-region optimiser with their iteration caps) still ends, and the ordinary instances next to them
+    get the ordinary answers"""
+    n = 2051
+    bad = np.arange(3, n, 41)
+    good = np.ones(n, dtype=bool)
+    good[bad] = False
+    S4 = synth.symmetric(n, 4, seed=0xBA1)
+    S4[bad, 5] = np.nan
+    d, z = mb.eig(4, dev(S4))
+    rd, _ = port.eig_sym(4, S4[good], True)
+    assert np.abs(d.cpu().numpy()[good] - rd).max() < 1e-12
+    S, M = synth.UR5_SCREWS, synth.UR5_HOME
+    kin = mb.Kinematics(S, M)
+    q = synth.joint_angles(n, seed=0xBA2)
+    Tt = port.poe_fk_jacobian(S, M, q + synth.ik_offsets(n), want_Js=False)[0]
+    qn, Tn = q.copy(), Tt.copy()
+    qn[bad[::2], 3] = np.nan
+    Tn[bad[1::2], 12] = np.nan
+    from matrix_b200 import _lib
+    for lu in (True, False):
+        _lib.set_square_solve_lu(lu)
+        try:
+            out = kin.ik_newton_step(dev(qn), dev(Tn)).cpu().numpy()
+        finally:
+            _lib.set_square_solve_lu(True)
+        ref = port.ik_newton_step(S, M, q[good], Tt[good])[0]
+        assert np.abs(out[good] - ref).max() < 1e-6 and not np.isfinite(out[bad]).all()
+    qs, it, st = kin.inverseSpaceNewton(dev(Tn), dev(qn), 20)
+    assert (st.cpu().numpy()[good] == mb.CONVERGED).mean() > 0.98 and int(it.max()) <= 20
+    lo, hi = -np.pi * np.ones(6), np.pi * np.ones(6)
+    qc, stc, fn = kin.inverseSpace(dev(Tn), dev(np.where(np.isfinite(qn), qn, 0.0) * 0.95), lo, hi)
+    torch.cuda.synchronize()
+    assert set(np.unique(stc.cpu().numpy())) <= {mb.CONVERGED, mb.DIVERGED}
+
+
 @pytest.mark.parametrize("layout", LAYOUTS)
 def test_linsolve_svd_6x6(mb, port, layout):
     n = 1 << 14
