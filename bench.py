@@ -277,7 +277,7 @@ def main():
         r = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
              "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "peak_source": peak_src, "kernel": cls.kernel,
              "kernel_ms": kernel_ms, "algorithmic_bytes_per_instance": cls.bytes_per_instance(),
-             "instances_per_launch": n_launch}
+             "instances_per_launch": n_launch, "expected_bound": cls.bound}
         c = counters.get(name) or counters.get(META[name].get("counters_as", ""), {})
         r["traffic"] = c.get("dram_bytes_per_launch") if c.get("instances") == n_launch else None
         r["traffic_source"] = (f"ncu --set full capture of the same kernel and batch size, {c.get('report', '?')} "
