@@ -1059,6 +1059,27 @@ def test_persistent_and_staged_kernels_stay_inside_their_buffers(mb, port, n):
         assert np.all(rel_err(inside(wi, 36), ref_inv) <= REL * np.maximum(1.0, kappa))
         assert np.all(rel_err(inside(wl, 6), ref_x) <= REL * np.maximum(1.0, kappa))
         assert torch.all(ist[:pad] == -3) and torch.all(ist[pad + n:] == -3) and torch.all(ist[pad:pad + n] == 0)
+        # round 2: MatrixS::operator* (an unrolled shape and the generic kernel) and the IK Newton step in both solve
+        # modes (for the UR5 these are the pattern kernels)
+        for (mm, nn, ll) in ((6, 6, 6), (5, 4, 2)):
+            Am, Bm = synth.dense(n, mm, nn, seed=0xD4), synth.dense(n, nn, ll, seed=0xD5)
+            wc, pc = canary(mm * ll)
+            dAm, dBm = put(Am), put(Bm)  # (kept alive past the launch)
+            _lib.check(lib.ppx_cuda_batch_matmul(mm, nn, ll, p(dAm), p(dBm), pc, n, layout, ld, None))
+            torch.cuda.synchronize()
+            assert np.array_equal(inside(wc, mm * ll), port.matmul(mm, nn, ll, Am, Bm))
+        ref_step = port.ik_newton_step(S, M, q, Tt)
+        for lu in (1, 0):
+            prev = lib.ppx_cuda_set_square_solve_lu(lu)
+            try:
+                wq, pq = canary(6)
+                wv, pv = canary(6)
+                _lib.check(lib.ppx_cuda_batch_ik_newton_step(vp(Sp), vp(Mp), 6, p(dq), p(dT), pq, pv, n, layout, ld, None))
+                torch.cuda.synchronize()
+            finally:
+                lib.ppx_cuda_set_square_solve_lu(prev)
+            assert rel_err(inside(wv, 6), ref_step[1]).max() < REL
+            assert np.abs(inside(wq, 6) - ref_step[0]).max() < 1e-6
 
 
 # --------------------------------------------------------------------------------------- square linsolve<SVD>: LU fast path
