@@ -133,9 +133,9 @@ int ppx_cuda_batch_so3_jac(int which, const double *w, double *J, size_t n, int 
  * q: njoints per instance;  T: 16 per instance or NULL;  Js: 6*njoints per instance or NULL. */
 int ppx_cuda_batch_poe_fk_jacobian(const double *screws, const double *home, int njoints, const double *q,
                                    double *T, double *Js, size_t n, int layout, size_t ld, void *stream);
-/* The three IK entry points below have kernels of their own for 6-joint chains whose joint axes follow one of two
- * patterns of unit coordinate axes (signs free): z y y y z y (the Universal-Robots family, the reference's fixture) and
- * z y y x y x (a spherical wrist in the home pose) -- the per-joint branch of the generic kernels is then resolved at
+/* The three IK entry points below have kernels of their own for 6-joint chains whose joint axes follow one of three
+ * patterns of unit coordinate axes (signs free): z y y y z y (the Universal-Robots family, the reference's fixture),
+ * z y y x y x and z y y z y z (a spherical wrist, forearm level or upright in the home pose) -- the per-joint branch of the generic kernels is then resolved at
  * compile time (Newton step +17 %, trust region +22 %, results bitwise equal for the Newton step and loop).  Every
  * other chain, and every chain when the environment variable PPX_IK_PATTERNS is 0, runs the generic kernels. */
 /* One Newton step of the reference's IK loop (test/lie_test.cpp:104-110):

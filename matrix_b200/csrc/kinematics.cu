@@ -143,6 +143,8 @@ __device__ __forceinline__ void ik_newton_update(const ChainConst<NJ> &ch, const
 // home pose (z y y x y x: PUMA, ABB IRB, KUKA KR, Fanuc, ...).  Any other chain runs the RuntimeKinds kernels.
 using KindsUR = FixedKinds<3, 2, 2, 2, 3, 2>;
 using KindsWrist = FixedKinds<3, 2, 2, 1, 2, 1>;
+// ... and the same arm drawn with its forearm pointing up in the home pose (z y y z y z: Denso, Epson, Staubli style)
+using KindsUpright = FixedKinds<3, 2, 2, 3, 2, 3>;
 
 template <int NJ, bool SVD_ONLY, class Kinds = RuntimeKinds>
 struct OpIkStep
@@ -432,6 +434,8 @@ typename std::enable_if<NJ == 6, int>::type ik_step_dispatch(const ChainConst<NJ
             return ik_step_launch<NJ, KindsUR>(ch, lu, q, Tt, q_out, Vs, n, layout, ld, stream);
         if (KindsWrist::matches(ch))
             return ik_step_launch<NJ, KindsWrist>(ch, lu, q, Tt, q_out, Vs, n, layout, ld, stream);
+        if (KindsUpright::matches(ch))
+            return ik_step_launch<NJ, KindsUpright>(ch, lu, q, Tt, q_out, Vs, n, layout, ld, stream);
     }
     return ik_step_launch<NJ, RuntimeKinds>(ch, lu, q, Tt, q_out, Vs, n, layout, ld, stream);
 }
@@ -576,6 +580,9 @@ int ppx_cuda_batch_ik_solve(const double *screws, const double *home, int njoint
     if (ik_patterns_enabled() && KindsWrist::matches(a.ch))
         return aos ? launch_persistent<ik_solve_kernel<LAYOUT_AOS, KindsWrist>>(128, 0, a, n, ld, stream)
                    : launch_persistent<ik_solve_kernel<LAYOUT_SOA, KindsWrist>>(128, 0, a, n, ld, stream);
+    if (ik_patterns_enabled() && KindsUpright::matches(a.ch))
+        return aos ? launch_persistent<ik_solve_kernel<LAYOUT_AOS, KindsUpright>>(128, 0, a, n, ld, stream)
+                   : launch_persistent<ik_solve_kernel<LAYOUT_SOA, KindsUpright>>(128, 0, a, n, ld, stream);
     return aos ? launch_persistent<ik_solve_kernel<LAYOUT_AOS, RuntimeKinds>>(128, 0, a, n, ld, stream)
                : launch_persistent<ik_solve_kernel<LAYOUT_SOA, RuntimeKinds>>(128, 0, a, n, ld, stream);
 }
@@ -608,6 +615,9 @@ int ppx_cuda_batch_ik_codo(const double *screws, const double *home, int njoints
     if (ik_patterns_enabled() && KindsWrist::matches(a.ch))
         return aos ? launch_persistent<ik_codo_kernel<LAYOUT_AOS, KindsWrist>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream)
                    : launch_persistent<ik_codo_kernel<LAYOUT_SOA, KindsWrist>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream);
+    if (ik_patterns_enabled() && KindsUpright::matches(a.ch))
+        return aos ? launch_persistent<ik_codo_kernel<LAYOUT_AOS, KindsUpright>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream)
+                   : launch_persistent<ik_codo_kernel<LAYOUT_SOA, KindsUpright>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream);
     return aos ? launch_persistent<ik_codo_kernel<LAYOUT_AOS, RuntimeKinds>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream)
                : launch_persistent<ik_codo_kernel<LAYOUT_SOA, RuntimeKinds>>(PPX_CODO_BLOCK, CODO_SMEM, a, n, ld, stream);
 }

@@ -266,14 +266,26 @@ WRIST_CHAIN = np.array([  # a 6R arm with a spherical wrist in its home pose: ax
 WRIST_HOME = np.array([0.0, 0.0, -1.0, 0.0, 0.0, 1.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.44, 1.0])
 
 
-@pytest.mark.parametrize("chain", ["ur5", "wrist"])
+UPRIGHT_CHAIN = np.array([  # the same kind of arm drawn with the forearm up in the home pose: axes z y y z y z
+    [0.0, 0.0, 1.0, 0.0, 0.0, 0.0],
+    [0.0, 1.0, 0.0, -0.35, 0.0, 0.05],
+    [0.0, -1.0, 0.0, 0.80, 0.0, -0.05],
+    [0.0, 0.0, 1.0, 0.0, -0.07, 0.0],
+    [0.0, 1.0, 0.0, -1.20, 0.0, 0.07],
+    [0.0, 0.0, -1.0, 0.0, 0.07, 0.0],
+])
+UPRIGHT_HOME = np.array([1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.07, 0.0, 1.30, 1.0])
+
+
+@pytest.mark.parametrize("chain", ["ur5", "wrist", "upright"])
 def test_pattern_kernels_match_the_generic_ones_and_the_oracle(mb, cpu_ref, chain):
     """Chains whose joint axes follow a precompiled pattern (FixedKinds: z y y y z y, z y y x y x) run IK kernels in
     which the per-joint branch is resolved at compile time; PPX_IK_PATTERNS=0 keeps them on the generic kernels.  Same
     arithmetic, so the two must agree bit for bit -- Newton step in both solve modes, and the whole Newton loop -- and
     both with the oracle."""
     from matrix_b200 import _lib
-    S, M = (synth.UR5_SCREWS, synth.UR5_HOME) if chain == "ur5" else (WRIST_CHAIN, WRIST_HOME)
+    S, M = {"ur5": (synth.UR5_SCREWS, synth.UR5_HOME), "wrist": (WRIST_CHAIN, WRIST_HOME),
+            "upright": (UPRIGHT_CHAIN, UPRIGHT_HOME)}[chain]
     n = 50_003
     q = synth.joint_angles(n, seed=0xC4B1)
     Tt = cpu_ref.poe_fk_jacobian(S, M, q + synth.ik_offsets(n), want_Js=False)[0]
