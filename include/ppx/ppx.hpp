@@ -685,6 +685,24 @@ void batch_mul(const Matrix<M, N> *A, const Matrix<N, L> *B, Matrix<M, L> *C, st
 inline void use_devices(const std::vector<int> &devices) { check(ppx_cuda_host_set_devices(devices.data(), (int)devices.size())); }
 inline void use_all_devices() { check(ppx_cuda_host_set_devices(nullptr, -1)); }
 inline void use_current_device() { check(ppx_cuda_host_set_devices(nullptr, 0)); }
+// measures the host links of all visible devices (ppx_cuda_host_tune_devices, ~3 s for 8 devices) and makes the subset
+// that carries the most together the device list; direction: 0 = calls dominated by inputs (H2D), 1 = by outputs (D2H),
+// 2 = balanced.  -> the chosen ordinals
+inline std::vector<int> tune_devices(int direction = 1, double seconds_per_probe = 0.15)
+{
+    const int have = ppx_cuda_device_count();
+    if (have < 1)
+        throw Error(PPX_ERR_NO_DEVICE);
+    const std::size_t bytes = (std::size_t)have * (256u << 20);
+    void *scratch = nullptr;
+    check(ppx_cuda_malloc_host(&scratch, bytes));
+    const int rc = ppx_cuda_host_tune_devices(nullptr, 0, scratch, bytes, direction, seconds_per_probe, nullptr);
+    ppx_cuda_free_host(scratch);
+    check(rc);
+    std::vector<int> devs(have);
+    devs.resize(ppx_cuda_host_get_devices(devs.data(), have));
+    return devs;
+}
 inline void batch_I(const SE3 *T, SE3 *Ti, std::size_t n) { check(ppx_cuda_host_SE3_inv(dp(T), dp(Ti), n)); }
 inline void batch_Adt(const SE3 *T, Matrix<6, 6> *Ad, std::size_t n) { check(ppx_cuda_host_SE3_Adt(dp(T), dp(Ad), n)); }
 inline void batch_adt(const se3 *xi, Matrix<6, 6> *ad, std::size_t n) { check(ppx_cuda_host_se3_adt(dp(xi), dp(ad), n)); }

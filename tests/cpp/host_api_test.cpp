@@ -185,6 +185,9 @@ int main()
         std::vector<Matrix<6, 6>> Js2(n);
         cuda::batch_fk_jacobian(UR5, q.data(), T2.data(), Js2.data(), n);
         cuda::use_current_device();
+        const std::vector<int> tuned = cuda::tune_devices(1, 0.05); // measured choice of devices: never empty
+        EXPECT(!tuned.empty());
+        cuda::use_current_device();
         bool bitwise = true;
         for (std::size_t i = 0; i < n; i++)
             bitwise = bitwise && std::equal(T[i].begin(), T[i].end(), T2[i].begin()) &&
