@@ -65,6 +65,8 @@ def config_for(workload, n, world):
     m = META[workload]
     per = m["bytes"] * n / 1e6
     return {"workload": workload, "instances_per_gpu": n,
+            "device_layout": {"records": "arrays of the reference's dense records (std::vector<MatrixS>)"}.get(
+                m.get("layout"), "component planes"),
             "chain": "UR5 (test/lie_test.cpp:187-196)" if m.get("chain") else None,
             "l2": f"inputs+outputs {per:.0f} MB per step >> 126 MB L2, every byte touched once per step",
             "parallelism": f"instance-sharded x{world}, no collective"}

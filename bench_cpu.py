@@ -210,7 +210,7 @@ def cpu_op(name, oracle, n):
 
 CPU = {
     "ur5_fk_jacobian": cpu_ur5_fk_jacobian,
-    "ur5_fk_jacobian_aos": cpu_ur5_fk_jacobian,
+    "ur5_fk_jacobian_planes": cpu_ur5_fk_jacobian,
     "se3_exp_log": cpu_se3_exp_log,
     "se3_exp_log_1M": cpu_se3_exp_log,
     "linsolve_qr_4x3": cpu_linsolve_qr_4x3,

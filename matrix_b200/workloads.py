@@ -103,9 +103,12 @@ class Workload:
 
 
 class Ur5FkJacobian(Workload):
-    """config 2: UR5 product-of-exponentials forward kinematics + space Jacobian"""
+    """config 2, the headline: UR5 product-of-exponentials forward kinematics + space Jacobian on device-resident arrays
+    of the reference's dense records (what a std::vector<MatrixS> holds) -- the layout the host face hands the kernel, so
+    `value`, `roofline` and `e2e` of the bench line describe one and the same kernel"""
     name = "ur5_fk_jacobian"
-    kernel = "batch_kernel_pf<SOA, OpFkJacobian<6, true, true>>"
+    kernel = "batch_kernel_pf<AOS, OpFkJacobian<6, true, true>>"
+    layout = "aos"
     n_default = 1 << 24
     bytes_in, bytes_out = 48, 128 + 288
     host_api = "ppx_cuda_host_poe_fk_jacobian"
@@ -113,14 +116,12 @@ class Ur5FkJacobian(Workload):
 
     def setup(self):
         self.kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
-        q = _device_records(self.n, 6, synth.SEEDS["ur5_fk_jacobian"], self.first, -np.pi, np.pi, self.device)
-        self.q = mb.to_soa(q)
-        del q
-        self.T = torch.empty((16, self.n), dtype=torch.float64, device=self.device)
-        self.Js = torch.empty((36, self.n), dtype=torch.float64, device=self.device)
+        self.q = _device_records(self.n, 6, synth.SEEDS["ur5_fk_jacobian"], self.first, -np.pi, np.pi, self.device)
+        self.T = torch.empty((self.n, 16), dtype=torch.float64, device=self.device)
+        self.Js = torch.empty((self.n, 36), dtype=torch.float64, device=self.device)
 
     def step(self):
-        self.kin.fk_jacobian(self.q, layout=mb.SOA, out_T=self.T, out_Js=self.Js)
+        self.kin.fk_jacobian(self.q, layout=mb.AOS, out_T=self.T, out_Js=self.Js)
 
     def free_outputs(self):
         self.T = self.Js = None
@@ -133,20 +134,22 @@ class Ur5FkJacobian(Workload):
                                                 _hp(outs[1]), n))
 
 
-class Ur5FkJacobianAoS(Ur5FkJacobian):
-    """config 2 on the drop-in layout: device-resident arrays of dense reference records (std::vector<MatrixS>)"""
-    name = "ur5_fk_jacobian_aos"
-    kernel = "batch_kernel_pf<AOS, OpFkJacobian<6, true, true>>"
-    layout = "aos"
+class Ur5FkJacobianPlanes(Ur5FkJacobian):
+    """config 2 on component planes (one plane per matrix element, the layout every other config is benched on)"""
+    name = "ur5_fk_jacobian_planes"
+    kernel = "batch_kernel_pf<SOA, OpFkJacobian<6, true, true>>"
+    layout = "soa"
 
     def setup(self):
         self.kin = mb.Kinematics(synth.UR5_SCREWS, synth.UR5_HOME)
-        self.q = _device_records(self.n, 6, synth.SEEDS["ur5_fk_jacobian"], self.first, -np.pi, np.pi, self.device)
-        self.T = torch.empty((self.n, 16), dtype=torch.float64, device=self.device)
-        self.Js = torch.empty((self.n, 36), dtype=torch.float64, device=self.device)
+        q = _device_records(self.n, 6, synth.SEEDS["ur5_fk_jacobian"], self.first, -np.pi, np.pi, self.device)
+        self.q = mb.to_soa(q)
+        del q
+        self.T = torch.empty((16, self.n), dtype=torch.float64, device=self.device)
+        self.Js = torch.empty((36, self.n), dtype=torch.float64, device=self.device)
 
     def step(self):
-        self.kin.fk_jacobian(self.q, layout=mb.AOS, out_T=self.T, out_Js=self.Js)
+        self.kin.fk_jacobian(self.q, layout=mb.SOA, out_T=self.T, out_Js=self.Js)
 
 
 def _twists_soa(n, first, device):
@@ -425,5 +428,5 @@ class IkCodo(Workload):
                                         _hp(ins[0]), _hp(ins[1]), _hp(outs[0]), None, _hp(outs[1]), _hp(outs[2]), n))
 
 
-WORKLOADS = {w.name: w for w in (Ur5FkJacobian, Ur5FkJacobianAoS, Se3ExpLog1M, Se3ExpLog, LinsolveQR43, Svd66, EigSym4,
+WORKLOADS = {w.name: w for w in (Ur5FkJacobian, Ur5FkJacobianPlanes, Se3ExpLog1M, Se3ExpLog, LinsolveQR43, Svd66, EigSym4,
                                  IkNewtonStep, IkNewtonStepSvd, IkCodo)}

@@ -179,3 +179,10 @@ def test_bench_tables_cover_every_baseline_config():
     for name, (n, nbytes) in want.items():
         assert META[name]["n"] == n and META[name]["bytes"] == nbytes and name in bench_cpu.CPU, name
     assert 8 * META["ik_newton_step"]["n"] == 1 << 28  # config 5: 256M instances over 8 GPUs
+    # the headline is benched on arrays of the reference's records (the kernel the host face launches as well), and
+    # what META says about a workload's device layout is what its class does
+    from matrix_b200 import workloads
+    from matrix_b200.workloads_meta import HEADLINE
+    assert META[HEADLINE]["layout"] == "records" and "AOS" in workloads.WORKLOADS[HEADLINE].kernel
+    for name, cls in workloads.WORKLOADS.items():
+        assert (cls.layout == "aos") == (META[name].get("layout") == "records"), name

@@ -1313,6 +1313,8 @@ def test_bench_prints_the_contract_line(mb):
     assert e["h2d_bytes_per_step"] == 1048576 * 48 and e["d2h_bytes_per_step"] == 1048576 * 416 and 0 < e["value"] < d["value"]
     assert e["result_probe"] == 1.0  # T[-1][15] of the end-to-end call's output: the result really arrived
     assert d["configs"][0]["workload"] == "ur5_fk_jacobian" and d["config"]["instances_per_gpu"] == 1048576
+    # the headline is the records kernel, the one the end-to-end call launches too
+    assert "AOS" in rf["kernel"] and d["layout"].startswith("aos") and "records" in d["config"]["device_layout"]
 
 
 def test_host_abi_is_thread_safe_and_keeps_its_scratch(mb, port):

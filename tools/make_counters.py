@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from matrix_b200.workloads_meta import META  # noqa: E402
 
-SIZES = {"ur5_fk_jacobian": 1 << 24, "ur5_fk_jacobian_aos": 1 << 24, "se3_exp_log": 1 << 26, "linsolve_qr_4x3": 1 << 26,
+SIZES = {"ur5_fk_jacobian": 1 << 24, "ur5_fk_jacobian_planes": 1 << 24, "se3_exp_log": 1 << 26, "linsolve_qr_4x3": 1 << 26,
          "svd_6x6": 1 << 24, "eig_sym_4": 1 << 24, "ik_newton_step": 1 << 25,
          "ik_newton_step_svd": 1 << 25}
 out = {}
