@@ -700,7 +700,10 @@ inline std::vector<int> tune_devices(int direction = 1, double seconds_per_probe
     ppx_cuda_free_host(scratch);
     check(rc);
     std::vector<int> devs(have);
-    devs.resize(ppx_cuda_host_get_devices(devs.data(), have));
+    const int count = ppx_cuda_host_get_devices(devs.data(), have);
+    if (count < 0)
+        throw Error(count);
+    devs.resize((std::size_t)count);
     return devs;
 }
 inline void batch_I(const SE3 *T, SE3 *Ti, std::size_t n) { check(ppx_cuda_host_SE3_inv(dp(T), dp(Ti), n)); }

@@ -49,6 +49,7 @@ extern "C" {
 #define PPX_ERR_BAD_SHAPE (-2)      /* (m, n) / njoints not compiled into this library */
 #define PPX_ERR_BAD_ARGUMENT (-3)   /* NULL pointer, ld < n, misaligned base, ... */
 #define PPX_ERR_NO_DEVICE (-4)
+#define PPX_ERR_HOST (-5)           /* host-side resource failure inside the library (worker thread, host memory) */
 
 #define PPX_STATUS_NORMAL 0
 #define PPX_STATUS_CONVERGED 1
@@ -203,7 +204,8 @@ int ppx_cuda_host_trim(void);
  * "0,1,2,...") says otherwise.  With several devices a call runs one worker thread per device and hands chunks of the
  * batch out from one shared queue, so the result is bitwise the one-device result whatever the split.  Process-wide. */
 int ppx_cuda_host_set_devices(const int *devices, int count);
-/* -> number of configured devices (0 = current device only); the first `capacity` ordinals are written to devices */
+/* -> number of configured devices (0 = current device only; < 0: a PPX_ERR_* code); the first `capacity` ordinals are
+ * written to devices */
 int ppx_cuda_host_get_devices(int *devices, int capacity);
 /* measurement helper: all configured devices copy at once through `host` (bytes, pinned) for `seconds`;
  * direction 0 H2D, 1 D2H, 2 both.  gbs[i] = GB/s device i sustained meanwhile: the ceiling of any host-buffer path. */

@@ -290,7 +290,7 @@ done:
 // chunk_mult: ops whose kernels have a long per-launch tail (the persistent trust-region / Newton-loop kernels: the
 // last stalled instance of a launch ends ~9 ms after the queue has drained) ask for larger chunks
 template <class Run>
-int pipeline(const std::vector<HostIn> &ins, const std::vector<HostOut> &outs, size_t n, Run run, size_t chunk_mult = 1)
+int pipeline_impl(const std::vector<HostIn> &ins, const std::vector<HostOut> &outs, size_t n, Run &run, size_t chunk_mult)
 {
     if (n == 0)
         return PPX_OK;
@@ -321,23 +321,52 @@ int pipeline(const std::vector<HostIn> &ins, const std::vector<HostOut> &outs, s
     // one worker per configured device, never more workers than chunks; the calling thread is the first of them
     const size_t workers = std::min<size_t>(devs.size(), job.nchunks);
     std::vector<std::thread> th;
-    for (size_t w = 1; w < workers; w++)
-        th.emplace_back([&job, &run, &devs, w] {
-            const cudaError_t se = cudaSetDevice(devs[w]);
-            if (se != cudaSuccess)
-                job.fail((int)se);
-            else
-                device_worker(job, run, true);
-        });
+    try
+    {
+        th.reserve(workers);
+        for (size_t w = 1; w < workers; w++)
+            th.emplace_back([&job, &run, &devs, w] {
+                try
+                {
+                    const cudaError_t se = cudaSetDevice(devs[w]);
+                    if (se != cudaSuccess)
+                        job.fail((int)se);
+                    else
+                        device_worker(job, run, true);
+                }
+                catch (...) // nothing may leave a worker thread
+                {
+                    job.fail(PPX_ERR_HOST);
+                }
+            });
+    }
+    catch (...) // a worker could not be started: the call fails, the workers already running stop at their next chunk
+    {
+        job.fail(PPX_ERR_HOST);
+    }
     e = cudaSetDevice(devs[0]);
     if (e != cudaSuccess)
         job.fail((int)e);
-    else
+    else if (job.rc.load() == PPX_OK)
         device_worker(job, run, workers > 1);
     for (std::thread &t : th)
         t.join();
     cudaSetDevice(home);
     return job.rc.load();
+}
+
+// C++ exceptions (std::bad_alloc, std::system_error) stop at the C boundary
+template <class Run>
+int pipeline(const std::vector<HostIn> &ins, const std::vector<HostOut> &outs, size_t n, Run run, size_t chunk_mult = 1)
+{
+    try
+    {
+        return pipeline_impl(ins, outs, n, run, chunk_mult);
+    }
+    catch (...)
+    {
+        return PPX_ERR_HOST;
+    }
 }
 
 // the copy loop behind ppx_cuda_host_copy_probe / ppx_cuda_host_tune_devices: all `devs` copy at once
@@ -411,9 +440,19 @@ int probe_devices(const std::vector<int> &devs, void *host, size_t bytes, int di
         }
     };
     std::vector<std::thread> th;
-    for (size_t w = 1; w < G; w++)
-        th.emplace_back(work, w);
-    work(0);
+    try
+    {
+        th.reserve(G);
+        for (size_t w = 1; w < G; w++)
+            th.emplace_back(work, w);
+        work(0);
+    }
+    catch (...) // a worker could not be started: release the ones spinning on the aligned start and report it
+    {
+        ready.fetch_add((int)G);
+        int ok = PPX_OK;
+        rc.compare_exchange_strong(ok, PPX_ERR_HOST);
+    }
     for (std::thread &t : th)
         t.join();
     cudaSetDevice(home);
@@ -432,6 +471,7 @@ extern "C"
 int ppx_cuda_host_trim(void) { return ppx_scratch_trim(); }
 
 int ppx_cuda_host_set_devices(const int *devices, int count)
+try
 {
     std::vector<int> v;
     if (count < 0) // all visible devices
@@ -461,13 +501,22 @@ int ppx_cuda_host_set_devices(const int *devices, int count)
     g_devices_set = true;
     return PPX_OK;
 }
+catch (...)
+{
+    return PPX_ERR_HOST;
+}
 
 int ppx_cuda_host_get_devices(int *devices, int capacity)
+try
 {
     const std::vector<int> v = host_devices();
     for (int i = 0; i < (int)v.size() && i < capacity && devices; i++)
         devices[i] = v[i];
     return (int)v.size();
+}
+catch (...)
+{
+    return PPX_ERR_HOST;
 }
 
 // Measurement helper: what the host-device links of the configured devices carry when all of them copy at once.
@@ -476,6 +525,7 @@ int ppx_cuda_host_get_devices(int *devices, int capacity)
 // workers starting together.  direction: 0 H2D, 1 D2H, 2 both at once (one stream each, on the two halves of the
 // slice).  gbs[i] = bytes device i moved / elapsed.  No kernel runs: this is the ceiling of any host-buffer path.
 int ppx_cuda_host_copy_probe(void *host, size_t bytes, int direction, double seconds, double *gbs)
+try
 {
     if (!host || !gbs || bytes == 0 || direction < 0 || direction > 2 || !(seconds > 0.0))
         return PPX_ERR_BAD_ARGUMENT;
@@ -490,6 +540,10 @@ int ppx_cuda_host_copy_probe(void *host, size_t bytes, int direction, double sec
     }
     return probe_devices(devs, host, bytes, direction, seconds, gbs);
 }
+catch (...)
+{
+    return PPX_ERR_HOST;
+}
 
 // Picks, among `candidates`, the devices whose host links carry the most WHEN USED TOGETHER and makes them the device
 // list of the host face.  On a multi-socket host the links are not independent: on the 8 x B200 box this was developed
@@ -501,6 +555,7 @@ int ppx_cuda_host_copy_probe(void *host, size_t bytes, int direction, double sec
 // solo rate -- until no addition gains 3 %.  ~20 probes for 8 devices.  *aggregate_gbs = rate of the chosen set.
 int ppx_cuda_host_tune_devices(const int *candidates, int count, void *host, size_t bytes, int direction, double seconds,
                                double *aggregate_gbs)
+try
 {
     if (!host || bytes == 0 || direction < 0 || direction > 2 || !(seconds > 0.0) || count > MAX_DEVICES)
         return PPX_ERR_BAD_ARGUMENT;
@@ -580,6 +635,10 @@ int ppx_cuda_host_tune_devices(const int *candidates, int count, void *host, siz
     g_devices = chosen;
     g_devices_set = true;
     return PPX_OK;
+}
+catch (...)
+{
+    return PPX_ERR_HOST;
 }
 
 int ppx_cuda_host_matmul(int m, int n, int l, const double *A, const double *B, double *C, size_t count)

@@ -175,6 +175,7 @@ const char *ppx_cuda_error_string(int code)
     case PPX_ERR_BAD_SHAPE: return "shape not compiled into libppx_cuda";
     case PPX_ERR_BAD_ARGUMENT: return "bad argument (null pointer, ld < n, out-of-range parameter)";
     case PPX_ERR_NO_DEVICE: return "no usable CUDA device";
+    case PPX_ERR_HOST: return "host-side resource failure (worker thread or host memory)";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown ppx error";
     }
 }

@@ -57,6 +57,8 @@ def set_devices(devices):
 def get_devices():
     arr = (C.c_int * 64)()
     n = lib.ppx_cuda_host_get_devices(arr, 64)
+    if n < 0:
+        check(n)
     return [arr[i] for i in range(n)]
 
 

@@ -37,6 +37,7 @@ def test_library_exports_every_declared_symbol():
     assert declared <= exported
     assert "sm_100a" in _lib.version()
     assert ctypes.c_char_p(_lib.lib.ppx_cuda_error_string(-2)).value.startswith(b"shape")
+    assert ctypes.c_char_p(_lib.lib.ppx_cuda_error_string(-5)).value.startswith(b"host-side")  # PPX_ERR_HOST
 
 
 def test_library_carries_sm_100a_code_only():
