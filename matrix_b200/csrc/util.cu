@@ -218,19 +218,35 @@ int ppx_cuda_malloc_host(void **hptr, size_t bytes)
             nt = nt == 0 ? 4 : (nt > 16 ? 16 : nt);
             const size_t slices = std::min<size_t>(nt, len / ((size_t)32 << 20) + 1);
             std::vector<std::thread> th;
-            for (size_t t = 0; t < slices; t++)
-                th.emplace_back([=] {
-                    const size_t lo = len / slices * t, hi = t + 1 == slices ? len : len / slices * (t + 1);
-                    for (size_t o = lo; o < hi; o += 4096)
-                        ((volatile char *)p)[o] = 0;
-                });
+            try // the parallel first touch is an optimisation: pages it does not reach are faulted by the registration
+            {
+                th.reserve(slices);
+                for (size_t t = 0; t < slices; t++)
+                    th.emplace_back([=] {
+                        const size_t lo = len / slices * t, hi = t + 1 == slices ? len : len / slices * (t + 1);
+                        for (size_t o = lo; o < hi; o += 4096)
+                            ((volatile char *)p)[o] = 0;
+                    });
+            }
+            catch (...)
+            {
+            }
             for (std::thread &t : th)
                 t.join();
             const cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable);
             if (e == cudaSuccess)
             {
-                std::lock_guard<std::mutex> lock(g_hb_mu);
-                g_hb[p] = HostBlock{raw, len + HUGE, len};
+                try
+                {
+                    std::lock_guard<std::mutex> lock(g_hb_mu);
+                    g_hb[p] = HostBlock{raw, len + HUGE, len};
+                }
+                catch (...)
+                {
+                    cudaHostUnregister(p);
+                    munmap(raw, len + HUGE);
+                    return PPX_ERR_HOST;
+                }
                 *hptr = p;
                 return PPX_OK;
             }
